@@ -1,0 +1,822 @@
+// cmpc_solver.h -- one NLP instance solved by one cooperative thread group (a CTA on the GPU).
+//
+// Replaces `self.opt.solve()` (code/centroidal_mpc_vertices.py:606: CasADi Opti -> IPOPT -> MUMPS) by a
+// primal-dual interior-point Newton method whose linear algebra is a stage-wise Riccati recursion:
+//
+//   eval pass      thread-per-stage: residuals, analytic Jacobians, barrier terms -> per-stage record
+//   backward pass  stage by stage, all threads: assemble the 60x60 stage KKT block in shared memory
+//                  (cost + barrier + Lagrangian Hessian + [B A]' P [B A]), partial Cholesky of the
+//                  32x32 input block, Schur complement = cost-to-go P_i; factors streamed to global
+//   forward pass   du_i = -L^-T (l_m + L_S' dx_i), dx_{i+1} = A dx_i + B du_i + d_i, costates
+//   line search    fraction-to-boundary + a short filter backtracking, evaluated thread-per-stage
+//   convergence    block-wide max/sum reductions (warp shuffles on the GPU)
+//
+// The code is written against an execution policy `Par` (tid, nt, sync, reductions) so the very same
+// source runs as one CTA per instance on sm_100a and as a single serial "thread" under g++ in
+// tests/hostsim (debug aid).  All arithmetic is FP64.
+#pragma once
+#include "cmpc_model.h"
+
+namespace cmpc {
+
+constexpr int LDM = NZ + 1;                 // leading dimension of the stage matrix (61, odd -> no bank conflicts)
+constexpr int MROWS = NZ + 1;               // 60 variable rows + the gradient row
+constexpr int TRI_U = NU * (NU + 1) / 2;    // 528
+constexpr int TRI_X = NX * (NX + 1) / 2;    // 406
+// per-stage factor record streamed to global memory
+constexpr int F_L = 0, F_LS = F_L + TRI_U, F_LM = F_LS + NX * NU, F_P = F_LM + NU, F_PV = F_P + TRI_X;
+constexpr int FACSZ = F_PV + NX;            // 1890 doubles
+// per-stage derivative record written by the eval pass
+constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
+              Q_LG = 556, Q_LC = 568, Q_LSIG = 584, Q_HP = 585, Q_HLAM = 588, Q_HSIG = 589, Q_YH = 590,
+              Q_GAM = 593, Q_GAMP = 595, Q_DR = 600;
+constexpr int RECSZ = 616;
+
+enum Status { ST_CONVERGED = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_INFEASIBLE_X0 = 4, ST_NAN = 5 };
+
+// Global-memory workspace of one instance (device resident across ticks: warm starts).
+struct Work {
+  double *X, *U, *Y, *S, *LAM;        // iterate: (N+1)*28, N*32, (N+1)*28, (N+1)*56, (N+1)*56
+  double *DX, *DU, *DS, *YN;          // Newton step (YN = full-step costates)
+  double *REC, *FAC;                  // (N+1)*RECSZ, N*FACSZ
+};
+
+CMPC_HD size_t work_doubles(int N) {
+  return (size_t)(N + 1) * NX * 4 + (size_t)N * NU * 2 + (size_t)(N + 1) * NR * 3 + (size_t)(N + 1) * RECSZ + (size_t)N * FACSZ;
+}
+
+CMPC_HD Work carve_work(double* base, int N) {
+  Work w; double* p = base;
+  w.X = p; p += (N + 1) * NX;  w.U = p; p += N * NU;  w.Y = p; p += (N + 1) * NX;
+  w.S = p; p += (N + 1) * NR;  w.LAM = p; p += (N + 1) * NR;
+  w.DX = p; p += (N + 1) * NX; w.DU = p; p += N * NU; w.DS = p; p += (N + 1) * NR; w.YN = p; p += (N + 1) * NX;
+  w.REC = p; p += (size_t)(N + 1) * RECSZ; w.FAC = p;
+  return w;
+}
+
+// Shared-memory block of one instance.
+struct Smem {
+  double M[MROWS * LDM];     // stage KKT block [u;x] (+ gradient row 60), lower triangle used
+  double W[NX * NZ];         // P * [B A]
+  double P[NX * NX];         // cost-to-go Hessian of stage i+1 (full symmetric)
+  double pv[NX];             // cost-to-go gradient
+  double tv[NX];             // p + P d
+  double bav[NZ * 4];        // sparse [B A] values of the current stage
+  double rec[RECSZ - Q_D];   // rest of the current record (d, diag, friction, Lyapunov, ...)
+  double dxs[NX], dxn[NX], zs[NU];
+  double red[40];
+  uint64_t mask[NMAX + 1];
+  double acc[NMAX + 1][8];   // per-stage partial results of eval / trial passes
+  int flag;
+};
+
+struct Stats { double cost, viol, kkt, mu; int iters, status, nfact, nreg; };
+
+// ---------------------------------------------------------------------------------------------
+// eval pass, one thread per stage: derivative record + KKT residual contributions.
+// acc[i] = {prim_inf, dual_inf, max s*lam, min s*lam, sum |y|+|lam|, cost(with reg), theta, sum ln s}
+CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, int i, uint64_t mask, double mu,
+                          double* acc) {
+  const int N = c.N;
+  const double* x = w.X + i * NX;
+  const double* s = w.S + i * NR;
+  const double* lam = w.LAM + i * NR;
+  double* rec = w.REC + (size_t)i * RECSZ;
+  double gc[NZ], m1[NZ], m2[NZ], gl_[NZ], diag[NZ];
+  for (int j = 0; j < NZ; ++j) { gc[j] = 0; m1[j] = 0; m2[j] = 0; gl_[j] = 0; diag[j] = 0; }
+  double prim = 0.0, smax = 0.0, smin = 1e300, lsum = 0.0, theta = 0.0, lns = 0.0;
+  double g[NR];
+  // helper: account one active row r with sparse Jacobian entries (idx, val) pairs
+  auto row = [&](int r, double gval, const int* idx, const double* val, int nnz) {
+    const double rg = gval - c.relax + s[r];
+    const double sig = lam[r] / s[r];
+    for (int t = 0; t < nnz; ++t) {
+      m1[idx[t]] += val[t] / s[r];
+      m2[idx[t]] += sig * rg * val[t];
+      gl_[idx[t]] += lam[r] * val[t];
+    }
+    const double ar = fabs(rg);
+    prim = ar > prim ? ar : prim; theta += ar; lns += log(s[r]);
+    const double sl = s[r] * lam[r];
+    smax = sl > smax ? sl : smax; smin = sl < smin ? sl : smin; lsum += lam[r];
+    return sig;
+  };
+
+  if (i >= 1) {                                                 // tracking cost of stage i (ref col i-1)
+    const double* ref = in.com_ref + 9 * (i - 1);
+    const double* fr = in.foot_ref + 8 * (i - 1);
+    const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+    const double wz = wz_of(c, i - 1);
+    gc[32 + 0] += 2.0 * c.w_xy * (x[0] - ref[0]); diag[32 + 0] += 2.0 * c.w_xy;
+    gc[32 + 1] += 2.0 * c.w_xy * (x[1] - ref[1]); diag[32 + 1] += 2.0 * c.w_xy;
+    gc[32 + 2] += 2.0 * wz * (x[2] - ref[2]);      diag[32 + 2] += 2.0 * wz;
+    for (int j = 0; j < 3; ++j) {
+      gc[32 + IPL + j] += 2.0 * c.w_foot * gl * (x[IPL + j] - fr[j]);     diag[32 + IPL + j] += 2.0 * c.w_foot * gl;
+      gc[32 + IPR + j] += 2.0 * c.w_foot * gr * (x[IPR + j] - fr[3 + j]); diag[32 + IPR + j] += 2.0 * c.w_foot * gr;
+    }
+    gc[32 + IPSL] += 2.0 * c.w_foot * gl * (x[IPSL] - fr[6]); diag[32 + IPSL] += 2.0 * c.w_foot * gl;
+    gc[32 + IPSR] += 2.0 * c.w_foot * gr * (x[IPSR] - fr[7]); diag[32 + IPSR] += 2.0 * c.w_foot * gr;
+    // box rows
+    for (int e = 0; e < 2; ++e) {
+      if (!(mask & (1ull << (R_BOX + 6 * e)))) continue;
+      for (int j = 0; j < 3; ++j) {
+        const int xi = 32 + (e ? IPR : IPL) + j;
+        const double err = x[(e ? IPR : IPL) + j] - fr[3 * e + j];
+        const double one = 1.0, mone = -1.0;
+        diag[xi] += row(R_BOX + 6 * e + 2 * j, err - c.box[j], &xi, &one, 1);
+        diag[xi] += row(R_BOX + 6 * e + 2 * j + 1, -err - c.box[j], &xi, &mone, 1);
+      }
+    }
+  }
+  if (mask & (1ull << R_PZ)) {
+    const int xi = 32 + IP + 2; const double one = 1.0;
+    diag[xi] += row(R_PZ, x[IP + 2] - c.pz_max, &xi, &one, 1);
+  }
+  double cost = (i >= 1) ? track_cost(c, in, i, x) : 0.0;
+  double dual = 0.0, ysum = 0.0;
+  if (i < N) {
+    const double* u = w.U + i * NU;
+    const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+    const double d = c.delta;
+    cost = stage_cost(c, in, i, x, u, true);
+    Arms a; lever_arms(c, x, a);
+    double* bav = rec + Q_BA;
+    ba_values(c, in, i, u, a, bav);
+    // --- cost gradient / diagonal Hessian of the input terms
+    for (int j = 0; j < 3; ++j) { gc[32 + IH + j] += 2.0 * c.w_h * x[IH + j]; diag[32 + IH + j] += 2.0 * c.w_h; }
+    for (int e = 0; e < 2; ++e) {
+      const double ge = e ? gr : gl;
+      const double gp = (i >= 1) ? in.gamma[2 * (i - 1) + e] * c.w_rate : 0.0;
+      const double* f = u + 12 * e;
+      double mean[3] = {0, 0, 0};
+      for (int k = 0; k < 4; ++k) for (int j = 0; j < 3; ++j) mean[j] += 0.25 * f[3 * k + j];
+      for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 3; ++j) {
+          const int ui = 12 * e + 3 * k + j;
+          gc[ui] += ge * 2.0 * c.w_sym * (f[3 * k + j] - mean[j]) + (1.0 - ge) * 2.0 * c.w_swing * f[3 * k + j];
+          diag[ui] += ge * 2.0 * c.w_sym * 0.75 + (1.0 - ge) * 2.0 * c.w_swing;
+          if (j == 2) {
+            const int qi = 32 + IQ + 4 * e + k;
+            const double dz = f[3 * k + 2] - x[IQ + 4 * e + k];
+            gc[ui] += 2.0 * gp * dz; gc[qi] -= 2.0 * gp * dz;
+            diag[ui] += 2.0 * gp; diag[qi] += 2.0 * gp;
+          }
+        }
+      rec[Q_GAM + e] = ge; rec[Q_GAMP + e] = gp;
+    }
+    for (int j = 24; j < 32; ++j) { gc[j] += 2.0 * c.eps_reg * u[j]; diag[j] += 2.0 * c.eps_reg; }
+    // --- friction / unilateral rows
+    for (int v = 0; v < 8; ++v) {
+      double* blk = rec + Q_FRIC + 6 * v;
+      for (int t = 0; t < 6; ++t) blk[t] = 0.0;
+      if (!(mask & (1ull << (R_UNI + v)))) continue;
+      const double* f = u + 3 * v;
+      const double mf = c.mu_fric;
+      int idx[2]; double val[2]; double sg[5];
+      idx[0] = 3 * v; idx[1] = 3 * v + 2; val[1] = -mf;
+      val[0] = 1.0;  sg[0] = row(R_FRIC + 4 * v + 0, f[0] - mf * f[2], idx, val, 2);
+      val[0] = -1.0; sg[1] = row(R_FRIC + 4 * v + 1, -f[0] - mf * f[2], idx, val, 2);
+      idx[0] = 3 * v + 1;
+      val[0] = 1.0;  sg[2] = row(R_FRIC + 4 * v + 2, f[1] - mf * f[2], idx, val, 2);
+      val[0] = -1.0; sg[3] = row(R_FRIC + 4 * v + 3, -f[1] - mf * f[2], idx, val, 2);
+      idx[0] = 3 * v + 2; val[0] = -1.0;
+      sg[4] = row(R_UNI + v, -f[2], idx, val, 1);
+      blk[0] = sg[0] + sg[1];                 // xx
+      blk[1] = 0.0;                           // xy
+      blk[2] = -mf * (sg[0] - sg[1]);         // xz
+      blk[3] = sg[2] + sg[3];                 // yy
+      blk[4] = -mf * (sg[2] - sg[3]);         // yz
+      blk[5] = mf * mf * (sg[0] + sg[1] + sg[2] + sg[3]) + sg[4];   // zz
+    }
+    // --- Lyapunov row
+    {
+      double F[3] = {0, 0, 0};
+      for (int v = 0; v < 8; ++v) {
+        const double ge = (v < 4) ? gl : gr;
+        F[0] += ge * u[3 * v]; F[1] += ge * u[3 * v + 1]; F[2] += ge * u[3 * v + 2];
+      }
+      double G[12], C[16];
+      const double q = lyapunov(c, in, i, x, F, G, C);
+      int idx[33]; double val[33]; int n = 0;
+      for (int v = 0; v < 8; ++v) {
+        const double ge = (v < 4) ? gl : gr;
+        if (ge < 0.5) continue;
+        for (int j = 0; j < 3; ++j) { idx[n] = 3 * v + j; val[n] = G[9 + j]; ++n; }
+      }
+      for (int j = 0; j < 3; ++j) { idx[n] = 32 + IP + j; val[n] = G[j]; ++n; }
+      for (int j = 0; j < 3; ++j) { idx[n] = 32 + IV + j; val[n] = G[3 + j]; ++n; }
+      for (int j = 0; j < 3; ++j) { idx[n] = 32 + ITH + j; val[n] = G[6 + j]; ++n; }
+      const double sig = row(R_LYAP, q, idx, val, n);
+      for (int t = 0; t < 12; ++t) rec[Q_LG + t] = G[t];
+      for (int t = 0; t < 16; ++t) rec[Q_LC + t] = lam[R_LYAP] * C[t];
+      rec[Q_LSIG] = sig;
+    }
+    // --- dynamics defect and predicted state
+    double xp[NX];
+    dyn_step(c, in, i, x, u, xp);
+    const double* xn = w.X + (i + 1) * NX;
+    for (int j = 0; j < NX; ++j) {
+      const double dj = xp[j] - xn[j];
+      rec[Q_D + j] = dj;
+      const double ad = fabs(dj);
+      prim = ad > prim ? ad : prim; theta += ad;
+    }
+    // --- angular momentum row (stage 0 only): ||h+||^2 - ||h||^2 <= 0, function of u only (x_0 fixed)
+    rec[Q_HLAM] = 0.0; rec[Q_HSIG] = 0.0;
+    if (mask & (1ull << R_HW)) {
+      const double ghw = xp[IH] * xp[IH] + xp[IH + 1] * xp[IH + 1] + xp[IH + 2] * xp[IH + 2]
+                       - (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]);
+      int idx[24]; double val[24];
+      for (int j = 0; j < 24; ++j) {
+        // d h+/d u_j : rows IH+(a+1)%3 (slot 1) and IH+(a+2)%3 (slot 2)
+        const int ax = j % 3;
+        idx[j] = j;
+        val[j] = 2.0 * (xp[IH + (ax + 1) % 3] * bav[4 * j + 1] + xp[IH + (ax + 2) % 3] * bav[4 * j + 2]);
+      }
+      const double sig = row(R_HW, ghw, idx, val, 24);
+      for (int j = 0; j < 3; ++j) rec[Q_HP + j] = xp[IH + j];
+      rec[Q_HLAM] = lam[R_HW]; rec[Q_HSIG] = sig;
+    }
+    // --- Lagrangian curvature of the bilinear torque term: y_h' (r x f)
+    const double* yn = w.Y + (i + 1) * NX;
+    for (int j = 0; j < 3; ++j) rec[Q_YH + j] = d * yn[IH + j];
+    for (int e = 0; e < 2; ++e) {
+      const double ge = e ? gr : gl;
+      double acc2 = 0.0;                  // -d*g * sum_k y . ((R c_k) x f_k)
+      for (int k = 0; k < 4; ++k) {
+        const int v = 4 * e + k; const double* f = u + 3 * v;
+        const double cx = a.rc[v][0], cy = a.rc[v][1];
+        acc2 += yn[IH] * (cy * f[2]) + yn[IH + 1] * (-cx * f[2]) + yn[IH + 2] * (cx * f[1] - cy * f[0]);
+      }
+      diag[32 + (e ? IPSR : IPSL)] += -d * ge * acc2;
+      // store R'c_k for the (f, psi) mixed terms
+      for (int k = 0; k < 4; ++k) { rec[Q_DR + 2 * (4 * e + k)] = a.dr[4 * e + k][0]; rec[Q_DR + 2 * (4 * e + k) + 1] = a.dr[4 * e + k][1]; }
+    }
+    // --- dual residual of stage i:  gc + J' lam + [B A]' y_{i+1} - [0; y_i]
+    for (int j = 0; j < NZ; ++j) {
+      double r = gc[j] + gl_[j];
+      for (int t = 0; t < 4; ++t) { const int rr = ba_row(j, t); if (rr >= 0) r += bav[4 * j + t] * yn[rr]; }
+      if (j >= 32) r -= w.Y[i * NX + (j - 32)];
+      if (i == 0 && j >= 32) r = 0.0;                      // x_0 is fixed
+      const double ar = fabs(r); dual = ar > dual ? ar : dual;
+    }
+  } else {
+    for (int j = 32; j < NZ; ++j) {
+      const double r = gc[j] + gl_[j] - w.Y[i * NX + (j - 32)];
+      const double ar = fabs(r); dual = ar > dual ? ar : dual;
+    }
+  }
+  for (int j = 0; j < NX; ++j) ysum += fabs(w.Y[i * NX + j]);
+  for (int j = 0; j < NZ; ++j) { rec[Q_GC + j] = gc[j]; rec[Q_M1 + j] = m1[j]; rec[Q_M2 + j] = m2[j]; rec[Q_DIAG + j] = diag[j]; }
+  acc[0] = prim; acc[1] = dual; acc[2] = smax; acc[3] = smin; acc[4] = ysum + lsum; acc[5] = cost; acc[6] = theta; acc[7] = lns;
+  (void)g; (void)mu;
+}
+
+// trial evaluation for the line search, one thread per stage: theta, cost, sum ln s at
+// (x + a dx, u + a du, s + a ds).  acc[i] = {theta, cost(with reg), sum ln s, max unrelaxed violation, cost(ref)}
+CMPC_HD void stage_trial(const Config& c, const Instance& in, const Work& w, int i, uint64_t mask, double alpha, double* acc) {
+  const int N = c.N;
+  double x[NX], u[NU], xn[NX], xp[NX], g[NR];
+  for (int j = 0; j < NX; ++j) x[j] = w.X[i * NX + j] + alpha * w.DX[i * NX + j];
+  double theta = 0.0, lns = 0.0, viol = 0.0;
+  if (i < N) {
+    for (int j = 0; j < NU; ++j) u[j] = w.U[i * NU + j] + alpha * w.DU[i * NU + j];
+    for (int j = 0; j < NX; ++j) xn[j] = w.X[(i + 1) * NX + j] + alpha * w.DX[(i + 1) * NX + j];
+    dyn_step(c, in, i, x, u, xp);
+    for (int j = 0; j < NX; ++j) { const double ad = fabs(xp[j] - xn[j]); theta += ad; viol = ad > viol ? ad : viol; }
+  } else {
+    for (int j = 0; j < NU; ++j) u[j] = 0.0;
+    for (int j = 0; j < NX; ++j) xp[j] = x[j];
+  }
+  stage_ineq(c, in, i, mask, x, u, xp, g);
+  for (int r = 0; r < NR; ++r) {
+    if (!(mask & (1ull << r))) continue;
+    const double st = w.S[i * NR + r] + alpha * w.DS[i * NR + r];
+    theta += fabs(g[r] - c.relax + st);
+    lns += log(st);
+    viol = g[r] > viol ? g[r] : viol;
+  }
+  acc[0] = theta; acc[1] = stage_cost(c, in, i, x, u, true); acc[2] = lns; acc[3] = viol;
+  acc[4] = stage_cost(c, in, i, x, u, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class Par>
+struct Solver {
+  const Config& c; const Instance& in; Work w; Smem& sm; Par& par;
+  double mu, reg_last;
+  int nfact, nreg;
+
+  CMPC_HD Solver(const Config& c_, const Instance& in_, const Work& w_, Smem& sm_, Par& par_)
+      : c(c_), in(in_), w(w_), sm(sm_), par(par_), mu(0), reg_last(0), nfact(0), nreg(0) {}
+
+  CMPC_HD static int tri(int r, int cidx) { return r * (r + 1) / 2 + cidx; }
+
+  // ---- initial point.  warm: 0 = cold (solver's own guess), 1 = primal (X, U given; slacks/duals reset as
+  // IPOPT does), 2 = full (X, U, Y, S, LAM given).
+  CMPC_HD void init_point(int warm) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    if (warm == 0) {
+      for (int t = tid; t < (N + 1) * NX; t += nt) {
+        const int i = t / NX, j = t % NX;
+        w.X[t] = (j < NXP) ? in.x0[j] : 0.0;
+        (void)i;
+      }
+      for (int t = tid; t < N * NU; t += nt) {
+        const int i = t / NU, j = t % NU;
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        double v = 0.0;
+        if (j < 24 && j % 3 == 2) {
+          const double ge = (j < 12) ? gl : gr;
+          v = ge * in.mass * c.grav / (4.0 * (gl + gr > 0.5 ? gl + gr : 1.0));
+        }
+        w.U[t] = v;
+      }
+      par.sync();
+      for (int t = tid; t < (N + 1) * NQ; t += nt) {
+        const int i = t / NQ, v = t % NQ;
+        w.X[i * NX + IQ + v] = (i >= 1) ? w.U[(i - 1) * NU + 3 * v + 2] : 0.0;
+      }
+    }
+    for (int t = tid; t < NX; t += nt) w.X[t] = (t < NXP) ? in.x0[t] : 0.0;      // x_0 is data
+    if (warm < 2) for (int t = tid; t < (N + 1) * NX; t += nt) w.Y[t] = 0.0;
+    par.sync();
+    if (warm < 2) {
+      mu = c.mu_init;
+      for (int i = tid; i <= N; i += nt) {
+        double x[NX], u[NU], xp[NX], g[NR];
+        for (int j = 0; j < NX; ++j) x[j] = w.X[i * NX + j];
+        if (i < N) { for (int j = 0; j < NU; ++j) u[j] = w.U[i * NU + j]; dyn_step(c, in, i, x, u, xp); }
+        else { for (int j = 0; j < NU; ++j) u[j] = 0.0; for (int j = 0; j < NX; ++j) xp[j] = x[j]; }
+        stage_ineq(c, in, i, sm.mask[i], x, u, xp, g);
+        for (int r = 0; r < NR; ++r) {
+          double sv = 1.0, lv = 0.0;
+          if (sm.mask[i] & (1ull << r)) { sv = -(g[r] - c.relax); sv = sv > c.bound_push ? sv : c.bound_push; lv = 1.0; }
+          w.S[i * NR + r] = sv; w.LAM[i * NR + r] = lv;
+        }
+      }
+    } else {
+      mu = c.mu_warm;
+      // keep the previous slacks/multipliers but push them off the boundary: s >= sqrt(mu)*1e-2, lam = mu/s floor
+      for (int t = tid; t < (N + 1) * NR; t += nt) {
+        const int i = t / NR, r = t % NR;
+        if (!(sm.mask[i] & (1ull << r))) { w.S[t] = 1.0; w.LAM[t] = 0.0; continue; }
+        double sv = w.S[t], lv = w.LAM[t];
+        if (!(sv > 1e-6)) sv = 1e-6;
+        if (!(lv > mu / sv * 1e-3)) lv = mu / sv * 1e-3;
+        w.S[t] = sv; w.LAM[t] = lv;
+      }
+    }
+    par.sync();
+  }
+
+  // ---- eval pass + reductions.  out: prim, dual, smax, smin, scale sums, cost, theta, lns
+  CMPC_HD void eval(double* out) {
+    const int N = c.N;
+    for (int i = par.tid(); i <= N; i += par.nt()) stage_derivs(c, in, w, i, sm.mask[i], mu, sm.acc[i]);
+    par.sync();
+    // tiny reduction over <= 61 stages done redundantly by every thread (broadcast reads)
+    double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0, cost = 0, theta = 0, lns = 0;
+    for (int i = 0; i <= N; ++i) {
+      const double* a = sm.acc[i];
+      prim = a[0] > prim ? a[0] : prim; dual = a[1] > dual ? a[1] : dual;
+      smax = a[2] > smax ? a[2] : smax; smin = a[3] < smin ? a[3] : smin;
+      ssum += a[4]; cost += a[5]; theta += a[6]; lns += a[7];
+    }
+    out[0] = prim; out[1] = dual; out[2] = smax; out[3] = smin; out[4] = ssum; out[5] = cost; out[6] = theta; out[7] = lns;
+    par.sync();
+  }
+
+  CMPC_HD int n_rows_total() const {
+    int n = 0;
+    for (int i = 0; i <= c.N; ++i) { uint64_t m = sm.mask[i]; while (m) { n += (int)(m & 1ull); m >>= 1; } }
+    return n;
+  }
+
+  // scaled optimality error of the barrier problem (IPOPT eq. 5/6)
+  CMPC_HD double kkt_error(const double* ev, double mu_t, int nrows, double* parts) const {
+    const double smax_ = 100.0;
+    const double nmult = (double)(nrows + (c.N + 1) * NX);
+    double sd = ev[4] / nmult; sd = (sd > smax_ ? sd : smax_) / smax_;
+    const double a = fabs(ev[2] - mu_t), b = fabs(ev[3] - mu_t);
+    const double compl_ = (nrows > 0) ? (a > b ? a : b) / sd : 0.0;
+    const double dual = ev[1] / sd;
+    parts[0] = dual; parts[1] = ev[0]; parts[2] = compl_;
+    double e = dual > ev[0] ? dual : ev[0];
+    return e > compl_ ? e : compl_;
+  }
+
+  // ---- backward Riccati sweep.  Returns false if a pivot of the input block is not positive.
+  CMPC_HD bool backward(double reg) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    // terminal stage: P_N = diag, p_N = modified gradient (x part)
+    {
+      const double* rec = w.REC + (size_t)N * RECSZ;
+      for (int t = tid; t < NX * NX; t += nt) {
+        const int r = t / NX, cc = t % NX;
+        sm.P[t] = (r == cc) ? rec[Q_DIAG + 32 + r] + reg : 0.0;
+      }
+      for (int t = tid; t < NX; t += nt) sm.pv[t] = rec[Q_GC + 32 + t] + mu * rec[Q_M1 + 32 + t] + rec[Q_M2 + 32 + t];
+      par.sync();
+    }
+    for (int i = N - 1; i >= 0; --i) {
+      const double* rec = w.REC + (size_t)i * RECSZ;
+      double* fac = w.FAC + (size_t)i * FACSZ;
+      // stage the record in shared memory; zero M; gradient row
+      for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
+      for (int t = tid; t < RECSZ - Q_D; t += nt) sm.rec[t] = rec[Q_D + t];
+      for (int t = tid; t < MROWS * LDM; t += nt) sm.M[t] = 0.0;
+      par.sync();
+      const double* R = sm.rec - Q_D;             // R[Q_xxx] addresses the staged record
+      for (int t = tid; t < NZ; t += nt) {
+        sm.M[NZ * LDM + t] = rec[Q_GC + t] + mu * rec[Q_M1 + t] + rec[Q_M2 + t];
+        sm.M[t * LDM + t] = R[Q_DIAG + t] + reg;
+      }
+      // friction barrier blocks (lower triangle)
+      for (int t = tid; t < 48; t += nt) {
+        const int v = t / 6, e6 = t % 6;
+        const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
+        const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
+        sm.M[(3 * v + rr) * LDM + 3 * v + cc] += R[Q_FRIC + t];
+      }
+      par.sync();
+      // symmetry-term off-diagonals (-2 w_sym / 4 between same-axis components of one foot) and rate cross terms
+      for (int t = tid; t < 36 + 8; t += nt) {
+        if (t < 36) {
+          const int e = t / 18, ax = (t % 18) / 6, pr = t % 6;
+          const int ka[6] = {1, 2, 2, 3, 3, 3}, kb[6] = {0, 0, 1, 0, 1, 2};
+          sm.M[(12 * e + 3 * ka[pr] + ax) * LDM + 12 * e + 3 * kb[pr] + ax] += -0.5 * c.w_sym * R[Q_GAM + e];
+        } else {
+          const int v = t - 36;
+          sm.M[(32 + IQ + v) * LDM + 3 * v + 2] += -2.0 * R[Q_GAMP + v / 4];
+        }
+      }
+      par.sync();
+      // Lyapunov row: sigma g g' + lam * C (x) I_3 over the 33 touched variables
+      {
+        const double sig = R[Q_LSIG];
+        for (int t = tid; t < 33 * 33; t += nt) {
+          const int ai = t / 33, bi = t % 33;
+          if (bi > ai) continue;
+          // index -> (M index, type, axis, scale)
+          int ma, ta, xa; double sa; int mb, tb, xb; double sb;
+          if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
+          else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = 32 + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
+          if (bi < 24) { mb = bi; tb = 3; xb = bi % 3; sb = R[Q_GAM + bi / 12]; }
+          else { const int q = bi - 24; tb = q / 3; xb = q % 3; sb = 1.0; mb = 32 + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xb; }
+          double v = sig * R[Q_LG + 3 * ta + xa] * R[Q_LG + 3 * tb + xb];
+          if (xa == xb) v += R[Q_LC + 4 * ta + tb];
+          v *= sa * sb;
+          if (ma >= mb) sm.M[ma * LDM + mb] += v; else sm.M[mb * LDM + ma] += v;
+        }
+      }
+      par.sync();
+      // angular-momentum row (stage 0): 2 lam Bh'Bh + sigma gh gh'
+      if (i == 0 && (sm.mask[0] & (1ull << R_HW))) {
+        const double lamh = R[Q_HLAM], sig = R[Q_HSIG];
+        for (int t = tid; t < 24 * 24; t += nt) {
+          const int a_ = t / 24, b_ = t % 24;
+          if (b_ > a_) continue;
+          // Bh column j: rows (ax+1)%3 -> slot1, (ax+2)%3 -> slot2
+          double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+          ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
+          cb[(b_ % 3 + 1) % 3] = sm.bav[4 * b_ + 1]; cb[(b_ % 3 + 2) % 3] = sm.bav[4 * b_ + 2];
+          const double dot = ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2];
+          const double ga = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
+          const double gb = 2.0 * (cb[0] * R[Q_HP] + cb[1] * R[Q_HP + 1] + cb[2] * R[Q_HP + 2]);
+          sm.M[a_ * LDM + b_] += 2.0 * lamh * dot + sig * ga * gb;
+        }
+        par.sync();
+      }
+      // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u)
+      {
+        const double y0 = R[Q_YH], y1 = R[Q_YH + 1], y2 = R[Q_YH + 2];      // delta * y_h
+        const double Yx[3][3] = {{0, -y2, y1}, {y2, 0, -y0}, {-y1, y0, 0}};
+        for (int t = tid; t < 8 * 21; t += nt) {
+          const int v = t / 21, q = t % 21, e = v / 4;
+          const double ge = R[Q_GAM + e];
+          if (q < 18) {
+            const int a_ = (q % 9) / 3, b_ = q % 3;
+            const double val = ge * Yx[a_][b_];
+            if (q < 9) sm.M[(32 + IP + b_) * LDM + 3 * v + a_] += -val;
+            else sm.M[(32 + (e ? IPR : IPL) + b_) * LDM + 3 * v + a_] += val;
+          } else {
+            const int a_ = q - 18;
+            const double dx_ = R[Q_DR + 2 * v], dy_ = R[Q_DR + 2 * v + 1];
+            // y x (R'c) with R'c = (dx_, dy_, 0)
+            const double cr[3] = {-y2 * dy_, y2 * dx_, y0 * dy_ - y1 * dx_};
+            sm.M[(32 + (e ? IPSR : IPSL)) * LDM + 3 * v + a_] += ge * cr[a_];
+          }
+        }
+      }
+      par.sync();
+      // W = P [B A]  (28 x 60);  tv = p + P d
+      for (int t = tid; t < NX * NZ; t += nt) {
+        const int r = t / NZ, j = t % NZ;
+        double s = 0.0;
+        for (int q = 0; q < 4; ++q) { const int rr = ba_row(j, q); if (rr >= 0) s += sm.P[r * NX + rr] * sm.bav[4 * j + q]; }
+        sm.W[t] = s;
+      }
+      for (int r = tid; r < NX; r += nt) {
+        double s = sm.pv[r];
+        for (int j = 0; j < NX; ++j) s += sm.P[r * NX + j] * R[Q_D + j];
+        sm.tv[r] = s;
+      }
+      par.sync();
+      // M += [B A]' W (lower triangle), gradient row += [B A]' tv
+      for (int t = tid; t < MROWS * NZ; t += nt) {
+        const int a_ = t / NZ, b_ = t % NZ;
+        if (a_ < NZ) {
+          if (b_ > a_) continue;
+          double s = 0.0;
+          for (int q = 0; q < 4; ++q) { const int rr = ba_row(a_, q); if (rr >= 0) s += sm.bav[4 * a_ + q] * sm.W[rr * NZ + b_]; }
+          sm.M[a_ * LDM + b_] += s;
+        } else {
+          double s = 0.0;
+          for (int q = 0; q < 4; ++q) { const int rr = ba_row(b_, q); if (rr >= 0) s += sm.bav[4 * b_ + q] * sm.tv[rr]; }
+          sm.M[NZ * LDM + b_] += s;
+        }
+      }
+      par.sync();
+      // partial Cholesky of the input block (right-looking), gradient row carried along
+      for (int k = 0; k < NU; ++k) {
+        const double piv = sm.M[k * LDM + k];
+        if (!(piv > 1e-14)) return false;                 // uniform: every thread reads the same value
+        const double inv = 1.0 / sqrt(piv);
+        par.sync();
+        for (int r = k + tid; r < MROWS; r += nt) sm.M[r * LDM + k] *= inv;      // M[k][k] becomes sqrt(piv)
+        par.sync();
+        const int nrem = MROWS - (k + 1), ncol = NZ - (k + 1);
+        for (int t = tid; t < nrem * ncol; t += nt) {
+          const int r = k + 1 + t / ncol, cc = k + 1 + t % ncol;
+          if (cc > r) continue;
+          sm.M[r * LDM + cc] -= sm.M[r * LDM + k] * sm.M[cc * LDM + k];
+        }
+        par.sync();
+      }
+      // stream factors out; load P, p for the next stage
+      for (int t = tid; t < NU * NU; t += nt) { const int r = t / NU, cc = t % NU; if (cc <= r) fac[F_L + tri(r, cc)] = sm.M[r * LDM + cc]; }
+      for (int t = tid; t < NX * NU; t += nt) { const int r = t / NU, cc = t % NU; fac[F_LS + t] = sm.M[(32 + r) * LDM + cc]; }
+      for (int t = tid; t < NU; t += nt) fac[F_LM + t] = sm.M[NZ * LDM + t];
+      for (int t = tid; t < NX * NX; t += nt) {
+        const int r = t / NX, cc = t % NX;
+        const double v = (cc <= r) ? sm.M[(32 + r) * LDM + 32 + cc] : sm.M[(32 + cc) * LDM + 32 + r];
+        sm.P[t] = v;
+        if (cc <= r) fac[F_P + tri(r, cc)] = v;
+      }
+      for (int t = tid; t < NX; t += nt) { const double v = sm.M[NZ * LDM + 32 + t]; sm.pv[t] = v; fac[F_PV + t] = v; }
+      par.sync();
+    }
+    return true;
+  }
+
+  // ---- forward sweep: Newton step (DX, DU), full-step costates YN, slack steps DS.
+  CMPC_HD void forward(double reg) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    for (int t = tid; t < NX; t += nt) { sm.dxs[t] = 0.0; w.DX[t] = 0.0; }
+    par.sync();
+    for (int i = 0; i < N; ++i) {
+      const double* fac = w.FAC + (size_t)i * FACSZ;
+      const double* rec = w.REC + (size_t)i * RECSZ;
+      for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
+      // L into M[0:32][0:32] (lower), zs = l_m + L_S' dx
+      for (int t = tid; t < NU * NU; t += nt) { const int r = t / NU, cc = t % NU; if (cc <= r) sm.M[r * LDM + cc] = fac[F_L + tri(r, cc)]; }
+      for (int cidx = tid; cidx < NU; cidx += nt) {
+        double s = fac[F_LM + cidx];
+        for (int r = 0; r < NX; ++r) s += fac[F_LS + r * NU + cidx] * sm.dxs[r];
+        sm.zs[cidx] = -s;
+      }
+      // costate of stage i (full step): y_i = p_i + P_i dx_i
+      for (int r = tid; r < NX; r += nt) {
+        double s = fac[F_PV + r];
+        for (int j = 0; j < NX; ++j) s += fac[F_P + (j <= r ? tri(r, j) : tri(j, r))] * sm.dxs[j];
+        w.YN[i * NX + r] = s;
+      }
+      for (int t = tid; t < NX; t += nt) sm.dxn[t] = rec[Q_D + t];
+      par.sync();
+      // back substitution L' du = zs (column oriented)
+      for (int k = NU - 1; k >= 0; --k) {
+        const double duk = sm.zs[k] / sm.M[k * LDM + k];
+        par.sync();
+        if (tid == 0) sm.zs[k] = duk;
+        for (int j = tid; j < k; j += nt) sm.zs[j] -= sm.M[k * LDM + j] * duk;
+        par.sync();
+      }
+      for (int t = tid; t < NU; t += nt) w.DU[i * NU + t] = sm.zs[t];
+      // dx_{i+1} = d + A dx + B du   (row-parallel over the structural pattern: gather form)
+      for (int r = tid; r < NX; r += nt) {
+        double s = sm.dxn[r];
+        for (int j = 0; j < NZ; ++j)
+          for (int q = 0; q < 4; ++q)
+            if (ba_row(j, q) == r) s += sm.bav[4 * j + q] * (j < 32 ? sm.zs[j] : sm.dxs[j - 32]);
+        sm.dxn[r] = s;
+      }
+      par.sync();
+      for (int t = tid; t < NX; t += nt) { sm.dxs[t] = sm.dxn[t]; w.DX[(i + 1) * NX + t] = sm.dxn[t]; }
+      par.sync();
+    }
+    // terminal costate: y_N = p_N + P_N dx_N  (P_N diagonal)
+    {
+      const double* rec = w.REC + (size_t)N * RECSZ;
+      for (int r = tid; r < NX; r += nt)
+        w.YN[N * NX + r] = rec[Q_GC + 32 + r] + mu * rec[Q_M1 + 32 + r] + rec[Q_M2 + 32 + r]
+                         + (rec[Q_DIAG + 32 + r] + reg) * sm.dxs[r];
+    }
+    par.sync();
+  }
+
+  // ---- slack steps ds = -(g - relax + s) - J dz, evaluated row by row; also the max step lengths.
+  // (thread-per-stage; uses the linearisation stored in the record through finite structure:
+  //  J dz is recomputed analytically row by row.)
+  CMPC_HD void slack_steps(double tau, double* a_p, double* a_d, double* dphi) {
+    const int N = c.N;
+    for (int i = par.tid(); i <= N; i += par.nt()) {
+      const uint64_t mask = sm.mask[i];
+      const double* x = w.X + i * NX; const double* dx = w.DX + i * NX;
+      const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR; double* ds = w.DS + i * NR;
+      const double* rec = w.REC + (size_t)i * RECSZ;
+      double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
+      double x_[NX], u_[NU], xp[NX], g[NR], jd[NR];
+      for (int j = 0; j < NX; ++j) x_[j] = x[j];
+      for (int r = 0; r < NR; ++r) jd[r] = 0.0;
+      if (i < N) {
+        const double* u = w.U + i * NU; const double* du = w.DU + i * NU;
+        for (int j = 0; j < NU; ++j) u_[j] = u[j];
+        dyn_step(c, in, i, x_, u_, xp);
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        // Lyapunov: gradient in xi-space from the record
+        double dF[3] = {0, 0, 0};
+        for (int v = 0; v < 8; ++v) { const double ge = (v < 4) ? gl : gr; for (int j = 0; j < 3; ++j) dF[j] += ge * du[3 * v + j]; }
+        for (int j = 0; j < 3; ++j)
+          jd[R_LYAP] += rec[Q_LG + j] * dx[IP + j] + rec[Q_LG + 3 + j] * dx[IV + j] + rec[Q_LG + 6 + j] * dx[ITH + j] + rec[Q_LG + 9 + j] * dF[j];
+        if (mask & (1ull << R_HW)) {
+          const double* bav = rec + Q_BA;
+          for (int j = 0; j < 24; ++j) {
+            const int ax = j % 3;
+            jd[R_HW] += 2.0 * (xp[IH + (ax + 1) % 3] * bav[4 * j + 1] + xp[IH + (ax + 2) % 3] * bav[4 * j + 2]) * du[j];
+          }
+        }
+        for (int v = 0; v < 8; ++v) {
+          const double* f = du + 3 * v; const double mf = c.mu_fric;
+          jd[R_FRIC + 4 * v + 0] = f[0] - mf * f[2]; jd[R_FRIC + 4 * v + 1] = -f[0] - mf * f[2];
+          jd[R_FRIC + 4 * v + 2] = f[1] - mf * f[2]; jd[R_FRIC + 4 * v + 3] = -f[1] - mf * f[2];
+          jd[R_UNI + v] = -f[2];
+        }
+        for (int j = 0; j < NU; ++j) gd += rec[Q_GC + j] * du[j];
+      } else {
+        for (int j = 0; j < NU; ++j) u_[j] = 0.0;
+        for (int j = 0; j < NX; ++j) xp[j] = x_[j];
+      }
+      jd[R_PZ] = dx[IP + 2];
+      for (int e = 0; e < 2; ++e)
+        for (int j = 0; j < 3; ++j) { const double v = dx[(e ? IPR : IPL) + j]; jd[R_BOX + 6 * e + 2 * j] = v; jd[R_BOX + 6 * e + 2 * j + 1] = -v; }
+      for (int j = 0; j < NX; ++j) gd += rec[Q_GC + 32 + j] * dx[j];
+      stage_ineq(c, in, i, mask, x_, u_, xp, g);
+      for (int r = 0; r < NR; ++r) {
+        if (!(mask & (1ull << r))) { ds[r] = 0.0; continue; }
+        const double dsr = -(g[r] - c.relax + s[r]) - jd[r];
+        ds[r] = dsr;
+        const double dl = -lam[r] + mu / s[r] - lam[r] / s[r] * dsr;
+        if (dsr < 0.0) { const double a = -tau * s[r] / dsr; ap = a < ap ? a : ap; }
+        if (dl < 0.0) { const double a = -tau * lam[r] / dl; ad = a < ad ? a : ad; }
+        dsos += dsr / s[r];
+      }
+      sm.acc[i][0] = ap; sm.acc[i][1] = ad; sm.acc[i][2] = gd; sm.acc[i][3] = dsos;
+    }
+    par.sync();
+    double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
+    for (int i = 0; i <= N; ++i) {
+      ap = sm.acc[i][0] < ap ? sm.acc[i][0] : ap; ad = sm.acc[i][1] < ad ? sm.acc[i][1] : ad;
+      gd += sm.acc[i][2]; dsos += sm.acc[i][3];
+    }
+    *a_p = ap; *a_d = ad; *dphi = gd - mu * dsos;
+    par.sync();
+  }
+
+  CMPC_HD void trial(double alpha, double* out) {
+    const int N = c.N;
+    for (int i = par.tid(); i <= N; i += par.nt()) stage_trial(c, in, w, i, sm.mask[i], alpha, sm.acc[i]);
+    par.sync();
+    double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
+    for (int i = 0; i <= N; ++i) {
+      theta += sm.acc[i][0]; cost += sm.acc[i][1]; lns += sm.acc[i][2];
+      viol = sm.acc[i][3] > viol ? sm.acc[i][3] : viol; cref += sm.acc[i][4];
+    }
+    out[0] = theta; out[1] = cost; out[2] = lns; out[3] = viol; out[4] = cref;
+    par.sync();
+  }
+
+  CMPC_HD void apply_step(double alpha, double a_d) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    for (int t = tid; t < (N + 1) * NX; t += nt) { w.X[t] += alpha * w.DX[t]; w.Y[t] += alpha * (w.YN[t] - w.Y[t]); }
+    for (int t = tid; t < N * NU; t += nt) w.U[t] += alpha * w.DU[t];
+    for (int t = tid; t < (N + 1) * NR; t += nt) {
+      const int i = t / NR, r = t % NR;
+      if (!(sm.mask[i] & (1ull << r))) continue;
+      const double s0 = w.S[t], l0 = w.LAM[t], dsr = w.DS[t];
+      const double dl = -l0 + mu / s0 - l0 / s0 * dsr;
+      double sn = s0 + alpha * dsr, ln = l0 + a_d * dl;
+      const double lo = mu / (1e10 * sn), hi = 1e10 * mu / sn;       // IPOPT eq. (16)
+      ln = ln < lo ? lo : (ln > hi ? hi : ln);
+      w.S[t] = sn; w.LAM[t] = ln;
+    }
+    par.sync();
+  }
+
+  // ---- the interior-point loop
+  CMPC_HD void run(int warm, Stats* st) {
+    const int N = c.N;
+    double pviol;
+    if (par.tid() == 0) { build_masks(c, in, sm.mask, &pviol); sm.red[0] = pviol; }
+    par.sync();
+    pviol = sm.red[0];
+    par.sync();
+    init_point(warm);
+    const int nrows = n_rows_total();
+    double ev[8], parts[3];
+    double filt[16][2]; int nfilt = 0;
+    double theta_max = 0, theta_min = 0; bool have_theta0 = false;
+    int status = ST_MAXITER, it = 0, ls_fail = 0;
+    double kkt = 0.0;
+    eval(ev);
+    for (it = 0; it <= c.max_iter; ++it) {
+      kkt = kkt_error(ev, c.mu_final, nrows, parts);
+      if (!(ev[0] == ev[0]) || !(ev[1] == ev[1]) || !(ev[5] == ev[5])) { status = ST_NAN; break; }
+      if (mu <= c.mu_final && kkt <= c.tol) { status = ST_CONVERGED; break; }
+      if (it == c.max_iter) break;
+      // monotone barrier update (IPOPT eq. 7)
+      while (mu > c.mu_final) {
+        double p2[3];
+        const double emu = kkt_error(ev, mu, nrows, p2);
+        if (emu > c.kappa_eps * mu) break;
+        double m1 = c.kappa_mu * mu, m2 = pow(mu, c.theta_mu);
+        mu = m1 < m2 ? m1 : m2; if (mu < c.mu_final) mu = c.mu_final;
+        nfilt = 0;
+      }
+      const double tau = (1.0 - mu) > c.tau_min ? (1.0 - mu) : c.tau_min;
+      // factorise, regularising as IPOPT does when the input block is not positive definite
+      double reg = 0.0; bool ok = false;
+      for (int attempt = 0; attempt < 40; ++attempt) {
+        ++nfact;
+        ok = backward(reg);
+        par.sync();
+        if (ok) break;
+        ++nreg;
+        if (reg == 0.0) reg = (reg_last == 0.0) ? 1e-4 : (reg_last / 3.0 > 1e-20 ? reg_last / 3.0 : 1e-20);
+        else reg *= (reg_last == 0.0) ? 100.0 : 8.0;
+        if (reg > 1e20) break;
+      }
+      if (!ok) { status = ST_REGULARIZATION; break; }
+      if (reg > 0.0) reg_last = reg;
+      forward(reg);
+      double a_p, a_d, dphi;
+      slack_steps(tau, &a_p, &a_d, &dphi);
+      // short filter line search (Waechter-Biegler eq. 18-20); falls back to the full
+      // fraction-to-boundary step if `ls_max` halvings are all rejected
+      const double theta = ev[6], phi = ev[5] - mu * ev[7];
+      if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * (theta > 1.0 ? theta : 1.0); theta_min = 1e-4 * (theta > 1.0 ? theta : 1.0); }
+      double alpha = a_p; bool accepted = false; double tr[5];
+      for (int ls = 0; ls < c.ls_max; ++ls) {
+        trial(alpha, tr);
+        const double th_t = tr[0], ph_t = tr[1] - mu * tr[2];
+        bool okf = (th_t == th_t) && (ph_t == ph_t) && th_t <= theta_max;
+        for (int f = 0; okf && f < nfilt; ++f) okf = (th_t < (1.0 - 1e-5) * filt[f][0]) || (ph_t < filt[f][1] - 1e-5 * filt[f][0]);
+        if (okf) {
+          const bool sw = theta <= theta_min && dphi < 0.0 && alpha * pow(-dphi, 2.3) > pow(theta, 1.1);
+          if (sw) {
+            if (ph_t <= phi + 1e-4 * alpha * dphi + 2.2e-15 * fabs(phi)) { accepted = true; break; }
+          } else if (th_t <= (1.0 - 1e-5) * theta || ph_t <= phi - 1e-5 * theta) {
+            accepted = true;
+            if (nfilt < 16) { filt[nfilt][0] = (1.0 - 1e-5) * theta; filt[nfilt][1] = phi - 1e-5 * theta; ++nfilt; }
+            break;
+          }
+        }
+        alpha *= 0.5;
+      }
+      if (!accepted) {
+        alpha = a_p;
+        trial(alpha, tr);
+        if (!(tr[0] == tr[0]) || !(tr[1] == tr[1]) || !(tr[2] == tr[2])) {
+          // the full step leaves the domain: shrink until finite
+          int k = 0;
+          for (; k < 30; ++k) { alpha *= 0.5; trial(alpha, tr); if (tr[0] == tr[0] && tr[1] == tr[1] && tr[2] == tr[2]) break; }
+          if (k == 30) { if (++ls_fail > 3) { status = ST_LINESEARCH; break; } }
+        }
+      }
+      apply_step(alpha, a_d);
+      eval(ev);
+    }
+    // final report: reference cost (no eps_reg term) and max unrelaxed violation incl. dynamics defects
+    double tr[5];
+    for (int t = par.tid(); t < (N + 1) * NX; t += par.nt()) w.DX[t] = 0.0;
+    for (int t = par.tid(); t < N * NU; t += par.nt()) w.DU[t] = 0.0;
+    for (int t = par.tid(); t < (N + 1) * NR; t += par.nt()) w.DS[t] = 0.0;
+    par.sync();
+    trial(0.0, tr);
+    if (status == ST_CONVERGED && pviol > 1e-6) status = ST_INFEASIBLE_X0;
+    st->cost = tr[4]; st->viol = tr[3] > pviol ? tr[3] : (pviol > 0 ? pviol : tr[3]);
+    st->kkt = kkt; st->mu = mu; st->iters = it; st->status = status; st->nfact = nfact; st->nreg = nreg;
+  }
+};
+
+}  // namespace cmpc
