@@ -1,0 +1,124 @@
+/* cmpc.h -- C ABI of the B200 batched centroidal-MPC solver (libcmpc_b200.so).
+ *
+ * Drop-in boundary for the per-tick NLP solve of the reference
+ * `code/centroidal_mpc_vertices.py` (and its `_payload` twin).  Each entry point replaces a group of
+ * CasADi calls made by `centroidal_mpc.solve` (file:line relative to /root/reference/code):
+ *
+ *   cmpc_create            <- cs.Opti() / opt.solver('ipopt', ...) / the whole NLP build
+ *                             (centroidal_mpc_vertices.py:126-353)
+ *   cmpc_solve_device/host <- opt.set_value x (x0, gamma_l, gamma_r, com_ref, 4N foot refs)
+ *                             (:511, :533-534, :590, :597-600), opt.solve() (:606),
+ *                             sol.value(state[:,1]), sol.value(U[:,0]) (:614-616)
+ *   cmpc_get_trajectory    <- sol.value(self.opti_state) / sol.value(self.U) (:617, :630-631)
+ *   cmpc_set_warm          <- opt.set_initial(U, ...), opt.set_initial(state, ...) (:630-631)
+ *   cmpc_reset_warm        <- a fresh Opti (first tick is solved from the solver's default guess)
+ *
+ * Batch-first: B independent instances per call, one CTA per instance, all FP64.  Instance-major
+ * layouts (each instance contiguous).  No torch types; plain pointers and sizes.  Every function
+ * returns 0 on success or a negative error code (never throws); cmpc_last_error() gives the text.
+ * A handle is bound to one GPU and is not re-entrant.
+ */
+#ifndef CMPC_H
+#define CMPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMPC_NX 20   /* states  (MPC file :164-166) */
+#define CMPC_NU 32   /* inputs  (MPC file :149-152) */
+
+/* per-instance status codes */
+enum {
+  CMPC_CONVERGED = 0,
+  CMPC_MAXITER = 1,
+  CMPC_LINESEARCH = 2,
+  CMPC_REGULARIZATION = 3,
+  CMPC_INFEASIBLE_X0 = 4,   /* a row that depends on x0 only is violated (e.g. CoM z > 0.76, :230) */
+  CMPC_NAN = 5
+};
+
+/* warm-start modes */
+enum {
+  CMPC_COLD = 0,          /* solver's own initial guess */
+  CMPC_WARM_PRIMAL = 1,   /* states/inputs of the previous solve (what the reference does, :630-631) */
+  CMPC_WARM_FULL = 2      /* states, inputs, costates, slacks and multipliers of the previous solve */
+};
+
+typedef struct cmpc_config {
+  int32_t N;              /* horizon, params['N'] (:10) */
+  int32_t max_iter;       /* interior-point iteration cap */
+  int32_t ls_max;         /* backtracking steps of the filter line search */
+  int32_t threads;        /* threads per instance (CTA size), multiple of 32 */
+  double delta;           /* world_time_step * mpc_rate (:11) */
+  double grav;            /* params['g'] (:18) */
+  double mu_fric;         /* 0.5 (:41) */
+  double foot_half_len;   /* 0.125 (:51) */
+  double foot_half_wid;   /* 0.065 (:52) */
+  double w_h, w_xy, w_zc, w_foot, w_sym, w_swing;   /* 1000, 1, 2000, 1000, 10, 10 (:301-335) */
+  double w_rate;          /* 1, or 0 when mpc_rate == 10 (:339-341) */
+  double eps_reg;         /* Tikhonov weight on the cost-free foot velocity / yaw-rate inputs */
+  double pz_max;          /* 0.76 (:230) */
+  double box[3];          /* 0.01, 0.005, 0.00005 (:259-271) */
+  double relax;           /* inequality relaxation, IPOPT bound_relax_factor = 1e-8 */
+  double mu_init, mu_final, mu_warm, tol;
+  double kappa_eps, kappa_mu, theta_mu, tau_min, bound_push;
+} cmpc_config;
+
+typedef struct cmpc_handle cmpc_handle;
+
+int cmpc_default_config(int32_t N, cmpc_config* cfg);
+int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, cmpc_handle** out);
+int cmpc_destroy(cmpc_handle* h);
+const char* cmpc_last_error(void);
+const char* cmpc_version(void);
+
+/* Solve `batch` instances.  All pointers are DEVICE pointers valid on the handle's GPU.
+ *   x0       [B][20]        opti_x0_param (:170)
+ *   com_ref  [B][N][9]      opti_com_ref column i = (pos, vel, acc) (:172)
+ *   foot_ref [B][N][8]      column i = (p_l(3), p_r(3), psi_l, psi_r) (:174-177)
+ *   gamma    [B][N+1][2]    (gamma_l, gamma_r) (:179-181)
+ *   mass,k1  [B]            params['mass'] (:15), k1 (:27; 7 in the payload variant)
+ * Outputs (device): x1 [B][20] = state[:,1]; u0 [B][32] = U[:,0]; xN [B][20] = state[:,N];
+ *   cost [B] (reference cost :311-351, without eps_reg term); viol [B] max unrelaxed violation of all
+ *   rows and dynamics defects; status/iters [B].  Any output pointer may be NULL.
+ * Asynchronous on `stream` (a cudaStream_t, may be NULL).  The warm-start state lives in the handle. */
+int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
+                      const double* foot_ref, const double* gamma, const double* mass, const double* k1,
+                      int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
+                      int32_t* status, int32_t* iters, void* stream);
+
+/* Same call with HOST buffers: pinned staging, H2D, solve, D2H, synchronises before returning. */
+int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
+                    const double* foot_ref, const double* gamma, const double* mass, const double* k1,
+                    int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
+                    int32_t* status, int32_t* iters);
+
+/* Full primal trajectories of the last solve to HOST buffers: X [B][N+1][20], U [B][N][32]. */
+int cmpc_get_trajectory(cmpc_handle* h, int32_t batch, double* X, double* U);
+/* Primal warm start from HOST buffers (same layouts); used with CMPC_WARM_PRIMAL. */
+int cmpc_set_warm(cmpc_handle* h, int32_t batch, const double* X, const double* U);
+/* Snapshot / restore the warm-start state (states, inputs, costates, slacks, multipliers) of the first `batch`
+ * instances inside the handle (device-to-device).  Lets a caller replay the same tick repeatedly (benchmarks,
+ * what-if sweeps from one nominal solution).  Restore is asynchronous on `stream` (may be NULL). */
+int cmpc_warm_save(cmpc_handle* h, int32_t batch);
+int cmpc_warm_restore(cmpc_handle* h, int32_t batch, void* stream);
+/* Forget the warm-start state of all instances. */
+int cmpc_reset_warm(cmpc_handle* h);
+/* Sum over the last batch of (interior-point iterations, Riccati factorisations, regularisation retries),
+ * device time of the last solve kernel in milliseconds (CUDA events) and kernels launched by it. */
+int cmpc_last_stats(cmpc_handle* h, int64_t* iters, int64_t* nfact, int64_t* nreg, double* kernel_ms,
+                    int32_t* launches);
+/* Bytes of device workspace per instance and shared memory per CTA. */
+int cmpc_footprint(const cmpc_handle* h, size_t* work_bytes_per_instance, size_t* smem_bytes_per_cta);
+
+/* Peak-FP64 probe: runs a dependent-free DFMA loop on every SM and returns the measured TFLOP/s. */
+int cmpc_measure_fp64_peak(int32_t device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMPC_H */

@@ -1,0 +1,17 @@
+"""B200-native batched solver for the per-tick centroidal NMPC of the reference
+(`code/centroidal_mpc_vertices.py`, `code/centroidal_mpc_vertices_payload.py`).
+
+Layout
+  csrc/            CUDA kernels + C ABI (include/cmpc.h) -> libcmpc_b200.so (built in-tree)
+  _lib.py          ctypes binding of the C ABI (`BatchSolver`)
+  assembly.py      per-tick parameter assembly of `solve` (MPC file :482-600), vectorised
+  centroidal_mpc_vertices.py / centroidal_mpc_vertices_payload.py
+                   drop-in modules with the reference's `centroidal_mpc` class surface
+
+There is no CPU path: creating a solver without the CUDA library or without a GPU raises.
+"""
+from ._lib import BatchSolver, CmpcError, build_library, library_path, measure_fp64_peak  # noqa: F401
+from .assembly import PlanTables, assemble_tick, pack_instances  # noqa: F401
+
+__all__ = ["BatchSolver", "CmpcError", "build_library", "library_path", "measure_fp64_peak",
+           "PlanTables", "assemble_tick", "pack_instances"]

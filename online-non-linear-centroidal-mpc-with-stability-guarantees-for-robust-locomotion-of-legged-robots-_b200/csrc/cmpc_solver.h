@@ -19,37 +19,47 @@
 
 namespace cmpc {
 
-constexpr int LDM = NZ + 1;                 // leading dimension of the stage matrix (61, odd -> no bank conflicts)
-constexpr int MROWS = NZ + 1;               // 60 variable rows + the gradient row
-constexpr int TRI_U = NU * (NU + 1) / 2;    // 528
+constexpr int NW = 2;                       // multipliers kept as explicit unknowns per stage (Lyapunov row, angular-momentum row)
+constexpr int NA = NU + NW;                 // 34: augmented input block [u ; w]
+constexpr int XO = NA;                      // offset of x in the stage block [u ; w ; x]
+constexpr int NZA = NA + NX;                // 62
+constexpr int GR = NZA;                     // index of the gradient row
+constexpr int LDM = NZA + 1;                // leading dimension of the stage matrix (63, odd -> no bank conflicts)
+constexpr int MROWS = NZA + 1;              // 62 variable rows + the gradient row
+constexpr int TRI_A = NA * (NA + 1) / 2;    // 595
 constexpr int TRI_X = NX * (NX + 1) / 2;    // 406
 // per-stage factor record streamed to global memory
-constexpr int F_L = 0, F_LS = F_L + TRI_U, F_LM = F_LS + NX * NU, F_P = F_LM + NU, F_PV = F_P + TRI_X;
-constexpr int FACSZ = F_PV + NX;            // 1890 doubles
+constexpr int F_L = 0, F_LS = F_L + TRI_A, F_LM = F_LS + NX * NA, F_P = F_LM + NA, F_PV = F_P + TRI_X;
+constexpr int FACSZ = F_PV + NX;            // 2015 doubles
 // per-stage derivative record written by the eval pass
 constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
               Q_LG = 556, Q_LC = 568, Q_LSIG = 584, Q_HP = 585, Q_HLAM = 588, Q_HSIG = 589, Q_YH = 590,
-              Q_GAM = 593, Q_GAMP = 595, Q_DR = 600;
-constexpr int RECSZ = 616;
+              Q_GAM = 593, Q_GAMP = 595, Q_DR = 600, Q_LRG = 616, Q_LLAM = 617, Q_HRG = 618;
+constexpr int RECSZ = 620;
+
+#ifdef CMPC_TRACE
+static int cmpc_trace_on = 0;
+static double cmpc_dbg_rd[64];
+#endif
 
 enum Status { ST_CONVERGED = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_INFEASIBLE_X0 = 4, ST_NAN = 5 };
 
 // Global-memory workspace of one instance (device resident across ticks: warm starts).
 struct Work {
   double *X, *U, *Y, *S, *LAM;        // iterate: (N+1)*28, N*32, (N+1)*28, (N+1)*56, (N+1)*56
-  double *DX, *DU, *DS, *YN;          // Newton step (YN = full-step costates)
+  double *DX, *DU, *DS, *YN, *DW;     // Newton step (YN = full-step costates, DW = new multipliers of explicit rows)
   double *REC, *FAC;                  // (N+1)*RECSZ, N*FACSZ
 };
 
 CMPC_HD size_t work_doubles(int N) {
-  return (size_t)(N + 1) * NX * 4 + (size_t)N * NU * 2 + (size_t)(N + 1) * NR * 3 + (size_t)(N + 1) * RECSZ + (size_t)N * FACSZ;
+  return (size_t)(N + 1) * NX * 4 + (size_t)N * NU * 2 + (size_t)N * NW + (size_t)(N + 1) * NR * 3 + (size_t)(N + 1) * RECSZ + (size_t)N * FACSZ;
 }
 
 CMPC_HD Work carve_work(double* base, int N) {
   Work w; double* p = base;
   w.X = p; p += (N + 1) * NX;  w.U = p; p += N * NU;  w.Y = p; p += (N + 1) * NX;
   w.S = p; p += (N + 1) * NR;  w.LAM = p; p += (N + 1) * NR;
-  w.DX = p; p += (N + 1) * NX; w.DU = p; p += N * NU; w.DS = p; p += (N + 1) * NR; w.YN = p; p += (N + 1) * NX;
+  w.DX = p; p += (N + 1) * NX; w.DU = p; p += N * NU; w.DS = p; p += (N + 1) * NR; w.YN = p; p += (N + 1) * NX; w.DW = p; p += N * NW;
   w.REC = p; p += (size_t)(N + 1) * RECSZ; w.FAC = p;
   return w;
 }
@@ -63,7 +73,7 @@ struct Smem {
   double tv[NX];             // p + P d
   double bav[NZ * 4];        // sparse [B A] values of the current stage
   double rec[RECSZ - Q_D];   // rest of the current record (d, diag, friction, Lyapunov, ...)
-  double dxs[NX], dxn[NX], zs[NU];
+  double dxs[NX], dxn[NX], zs[NA];
   double red[40];
   uint64_t mask[NMAX + 1];
   double acc[NMAX + 1][8];   // per-stage partial results of eval / trial passes
@@ -87,12 +97,11 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
   double prim = 0.0, smax = 0.0, smin = 1e300, lsum = 0.0, theta = 0.0, lns = 0.0;
   double g[NR];
   // helper: account one active row r with sparse Jacobian entries (idx, val) pairs
-  auto row = [&](int r, double gval, const int* idx, const double* val, int nnz) {
+  auto row = [&](int r, double gval, const int* idx, const double* val, int nnz, bool explicit_row = false) {
     const double rg = gval - c.relax + s[r];
     const double sig = lam[r] / s[r];
     for (int t = 0; t < nnz; ++t) {
-      m1[idx[t]] += val[t] / s[r];
-      m2[idx[t]] += sig * rg * val[t];
+      if (!explicit_row) { m1[idx[t]] += val[t] / s[r]; m2[idx[t]] += sig * rg * val[t]; }
       gl_[idx[t]] += lam[r] * val[t];
     }
     const double ar = fabs(rg);
@@ -206,7 +215,8 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
       for (int j = 0; j < 3; ++j) { idx[n] = 32 + IP + j; val[n] = G[j]; ++n; }
       for (int j = 0; j < 3; ++j) { idx[n] = 32 + IV + j; val[n] = G[3 + j]; ++n; }
       for (int j = 0; j < 3; ++j) { idx[n] = 32 + ITH + j; val[n] = G[6 + j]; ++n; }
-      const double sig = row(R_LYAP, q, idx, val, n);
+      const double sig = row(R_LYAP, q, idx, val, n, true);
+      rec[Q_LRG] = q - c.relax + s[R_LYAP]; rec[Q_LLAM] = lam[R_LYAP];
       for (int t = 0; t < 12; ++t) rec[Q_LG + t] = G[t];
       for (int t = 0; t < 16; ++t) rec[Q_LC + t] = lam[R_LYAP] * C[t];
       rec[Q_LSIG] = sig;
@@ -233,7 +243,8 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
         idx[j] = j;
         val[j] = 2.0 * (xp[IH + (ax + 1) % 3] * bav[4 * j + 1] + xp[IH + (ax + 2) % 3] * bav[4 * j + 2]);
       }
-      const double sig = row(R_HW, ghw, idx, val, 24);
+      const double sig = row(R_HW, ghw, idx, val, 24, true);
+      rec[Q_HRG] = ghw - c.relax + s[R_HW];
       for (int j = 0; j < 3; ++j) rec[Q_HP + j] = xp[IH + j];
       rec[Q_HLAM] = lam[R_HW]; rec[Q_HSIG] = sig;
     }
@@ -259,6 +270,9 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
       if (j >= 32) r -= w.Y[i * NX + (j - 32)];
       if (i == 0 && j >= 32) r = 0.0;                      // x_0 is fixed
       const double ar = fabs(r); dual = ar > dual ? ar : dual;
+#ifdef CMPC_TRACE
+      cmpc_dbg_rd[j] = r;
+#endif
     }
   } else {
     for (int j = 32; j < NZ; ++j) {
@@ -406,11 +420,124 @@ struct Solver {
     return e > compl_ ? e : compl_;
   }
 
-  // ---- backward Riccati sweep.  Returns false if a pivot of the input block is not positive.
+  // M index of stage variable j of the 60-ordering z = [u ; x]  (block ordering is [u ; w ; x])
+  CMPC_HD static int mz(int j) { return j < NU ? j : j + NW; }
+
+  // ---- stage KKT block of stage i without the cost-to-go term: cost + barrier + Lagrangian curvature.
+  // The Lyapunov row and the angular-momentum row touch many variables and carry multipliers of 1e3..1e6;
+  // condensing them (sigma g g', sigma = lam/s up to 1e18) would destroy the Schur complements by
+  // cancellation, so their new multipliers w stay explicit unknowns of the (quasi-definite) stage block:
+  //   [ H   g ] [dz]   [ -grad          ]
+  //   [ g' -1/sigma ] [w ] = [ -(r_g + mu/lam) ]
+  CMPC_HD void assemble_stage(int i, double reg) {
+    const int tid = par.tid(), nt = par.nt();
+    const double* rec = w.REC + (size_t)i * RECSZ;
+    for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
+    for (int t = tid; t < RECSZ - Q_D; t += nt) sm.rec[t] = rec[Q_D + t];
+    for (int t = tid; t < MROWS * LDM; t += nt) sm.M[t] = 0.0;
+    par.sync();
+    const double* R = sm.rec - Q_D;             // R[Q_xxx] addresses the staged record
+    const bool has_hw = (i == 0) && (sm.mask[0] & (1ull << R_HW));
+    for (int t = tid; t < NZ; t += nt) {
+      sm.M[GR * LDM + mz(t)] = rec[Q_GC + t] + mu * rec[Q_M1 + t] + rec[Q_M2 + t];
+      sm.M[mz(t) * LDM + mz(t)] = R[Q_DIAG + t] + reg;
+    }
+    if (tid == 0) {
+      sm.M[NU * LDM + NU] = -1.0 / R[Q_LSIG];
+      sm.M[GR * LDM + NU] = R[Q_LRG] + mu / R[Q_LLAM];
+      sm.M[(NU + 1) * LDM + NU + 1] = has_hw ? -1.0 / R[Q_HSIG] : -1.0;
+      sm.M[GR * LDM + NU + 1] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
+    }
+    // friction barrier blocks (lower triangle)
+    for (int t = tid; t < 48; t += nt) {
+      const int v = t / 6, e6 = t % 6;
+      const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
+      const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
+      sm.M[(3 * v + rr) * LDM + 3 * v + cc] += R[Q_FRIC + t];
+    }
+    par.sync();
+    // symmetry-term off-diagonals (-2 w_sym / 4 between same-axis components of one foot) and rate cross terms
+    for (int t = tid; t < 36 + 8; t += nt) {
+      if (t < 36) {
+        const int e = t / 18, ax = (t % 18) / 6, pr = t % 6;
+        const int ka[6] = {1, 2, 2, 3, 3, 3}, kb[6] = {0, 0, 1, 0, 1, 2};
+        sm.M[(12 * e + 3 * ka[pr] + ax) * LDM + 12 * e + 3 * kb[pr] + ax] += -0.5 * c.w_sym * R[Q_GAM + e];
+      } else {
+        const int v = t - 36;
+        sm.M[(XO + IQ + v) * LDM + 3 * v + 2] += -2.0 * R[Q_GAMP + v / 4];
+      }
+    }
+    par.sync();
+    // Lyapunov row: lam * C (x) I_3 curvature over the 33 touched variables, and its gradient as row/column NU
+    for (int t = tid; t < 33 * 33 + 33; t += nt) {
+      if (t >= 33 * 33) {
+        const int ai = t - 33 * 33;
+        int ma, ta, xa; double sa;
+        if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
+        else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
+        const double gv = sa * R[Q_LG + 3 * ta + xa];
+        if (ma < NU) sm.M[NU * LDM + ma] = gv; else sm.M[ma * LDM + NU] = gv;
+        continue;
+      }
+      const int ai = t / 33, bi = t % 33;
+      if (bi > ai) continue;
+      int ma, ta, xa; double sa; int mb, tb, xb; double sb;
+      if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
+      else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
+      if (bi < 24) { mb = bi; tb = 3; xb = bi % 3; sb = R[Q_GAM + bi / 12]; }
+      else { const int q = bi - 24; tb = q / 3; xb = q % 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xb; }
+      if (xa != xb) continue;
+      const double v = sa * sb * R[Q_LC + 4 * ta + tb];
+      if (ma >= mb) sm.M[ma * LDM + mb] += v; else sm.M[mb * LDM + ma] += v;
+    }
+    par.sync();
+    // angular-momentum row (stage 0): curvature 2 lam Bh'Bh in the force block, gradient as row NU+1
+    if (has_hw) {
+      const double lamh = R[Q_HLAM];
+      for (int t = tid; t < 24 * 24 + 24; t += nt) {
+        if (t >= 24 * 24) {
+          const int a_ = t - 24 * 24;
+          double ca[3] = {0, 0, 0};
+          ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
+          sm.M[(NU + 1) * LDM + a_] = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
+          continue;
+        }
+        const int a_ = t / 24, b_ = t % 24;
+        if (b_ > a_) continue;
+        double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+        ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
+        cb[(b_ % 3 + 1) % 3] = sm.bav[4 * b_ + 1]; cb[(b_ % 3 + 2) % 3] = sm.bav[4 * b_ + 2];
+        sm.M[a_ * LDM + b_] += 2.0 * lamh * (ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2]);
+      }
+      par.sync();
+    }
+    // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u)
+    {
+      const double y0 = R[Q_YH], y1 = R[Q_YH + 1], y2 = R[Q_YH + 2];      // delta * y_h
+      const double Yx[3][3] = {{0, -y2, y1}, {y2, 0, -y0}, {-y1, y0, 0}};
+      for (int t = tid; t < 8 * 21; t += nt) {
+        const int v = t / 21, q = t % 21, e = v / 4;
+        const double ge = R[Q_GAM + e];
+        if (q < 18) {
+          const int a_ = (q % 9) / 3, b_ = q % 3;
+          const double val = ge * Yx[a_][b_];
+          if (q < 9) sm.M[(XO + IP + b_) * LDM + 3 * v + a_] += -val;
+          else sm.M[(XO + (e ? IPR : IPL) + b_) * LDM + 3 * v + a_] += val;
+        } else {
+          const int a_ = q - 18;
+          const double dx_ = R[Q_DR + 2 * v], dy_ = R[Q_DR + 2 * v + 1];
+          const double cr[3] = {-y2 * dy_, y2 * dx_, y0 * dy_ - y1 * dx_};   // y x (R'c), R'c = (dx_, dy_, 0)
+          sm.M[(XO + (e ? IPSR : IPSL)) * LDM + 3 * v + a_] += ge * cr[a_];
+        }
+      }
+    }
+    par.sync();
+  }
+
+  // ---- backward Riccati sweep.  Returns false if a pivot has the wrong sign (inputs > 0, multipliers < 0).
   CMPC_HD bool backward(double reg) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
-    // terminal stage: P_N = diag, p_N = modified gradient (x part)
-    {
+    {   // terminal stage: P_N diagonal, p_N = modified gradient (x part)
       const double* rec = w.REC + (size_t)N * RECSZ;
       for (int t = tid; t < NX * NX; t += nt) {
         const int r = t / NX, cc = t % NX;
@@ -420,96 +547,9 @@ struct Solver {
       par.sync();
     }
     for (int i = N - 1; i >= 0; --i) {
-      const double* rec = w.REC + (size_t)i * RECSZ;
       double* fac = w.FAC + (size_t)i * FACSZ;
-      // stage the record in shared memory; zero M; gradient row
-      for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
-      for (int t = tid; t < RECSZ - Q_D; t += nt) sm.rec[t] = rec[Q_D + t];
-      for (int t = tid; t < MROWS * LDM; t += nt) sm.M[t] = 0.0;
-      par.sync();
-      const double* R = sm.rec - Q_D;             // R[Q_xxx] addresses the staged record
-      for (int t = tid; t < NZ; t += nt) {
-        sm.M[NZ * LDM + t] = rec[Q_GC + t] + mu * rec[Q_M1 + t] + rec[Q_M2 + t];
-        sm.M[t * LDM + t] = R[Q_DIAG + t] + reg;
-      }
-      // friction barrier blocks (lower triangle)
-      for (int t = tid; t < 48; t += nt) {
-        const int v = t / 6, e6 = t % 6;
-        const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
-        const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
-        sm.M[(3 * v + rr) * LDM + 3 * v + cc] += R[Q_FRIC + t];
-      }
-      par.sync();
-      // symmetry-term off-diagonals (-2 w_sym / 4 between same-axis components of one foot) and rate cross terms
-      for (int t = tid; t < 36 + 8; t += nt) {
-        if (t < 36) {
-          const int e = t / 18, ax = (t % 18) / 6, pr = t % 6;
-          const int ka[6] = {1, 2, 2, 3, 3, 3}, kb[6] = {0, 0, 1, 0, 1, 2};
-          sm.M[(12 * e + 3 * ka[pr] + ax) * LDM + 12 * e + 3 * kb[pr] + ax] += -0.5 * c.w_sym * R[Q_GAM + e];
-        } else {
-          const int v = t - 36;
-          sm.M[(32 + IQ + v) * LDM + 3 * v + 2] += -2.0 * R[Q_GAMP + v / 4];
-        }
-      }
-      par.sync();
-      // Lyapunov row: sigma g g' + lam * C (x) I_3 over the 33 touched variables
-      {
-        const double sig = R[Q_LSIG];
-        for (int t = tid; t < 33 * 33; t += nt) {
-          const int ai = t / 33, bi = t % 33;
-          if (bi > ai) continue;
-          // index -> (M index, type, axis, scale)
-          int ma, ta, xa; double sa; int mb, tb, xb; double sb;
-          if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
-          else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = 32 + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
-          if (bi < 24) { mb = bi; tb = 3; xb = bi % 3; sb = R[Q_GAM + bi / 12]; }
-          else { const int q = bi - 24; tb = q / 3; xb = q % 3; sb = 1.0; mb = 32 + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xb; }
-          double v = sig * R[Q_LG + 3 * ta + xa] * R[Q_LG + 3 * tb + xb];
-          if (xa == xb) v += R[Q_LC + 4 * ta + tb];
-          v *= sa * sb;
-          if (ma >= mb) sm.M[ma * LDM + mb] += v; else sm.M[mb * LDM + ma] += v;
-        }
-      }
-      par.sync();
-      // angular-momentum row (stage 0): 2 lam Bh'Bh + sigma gh gh'
-      if (i == 0 && (sm.mask[0] & (1ull << R_HW))) {
-        const double lamh = R[Q_HLAM], sig = R[Q_HSIG];
-        for (int t = tid; t < 24 * 24; t += nt) {
-          const int a_ = t / 24, b_ = t % 24;
-          if (b_ > a_) continue;
-          // Bh column j: rows (ax+1)%3 -> slot1, (ax+2)%3 -> slot2
-          double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
-          ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
-          cb[(b_ % 3 + 1) % 3] = sm.bav[4 * b_ + 1]; cb[(b_ % 3 + 2) % 3] = sm.bav[4 * b_ + 2];
-          const double dot = ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2];
-          const double ga = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
-          const double gb = 2.0 * (cb[0] * R[Q_HP] + cb[1] * R[Q_HP + 1] + cb[2] * R[Q_HP + 2]);
-          sm.M[a_ * LDM + b_] += 2.0 * lamh * dot + sig * ga * gb;
-        }
-        par.sync();
-      }
-      // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u)
-      {
-        const double y0 = R[Q_YH], y1 = R[Q_YH + 1], y2 = R[Q_YH + 2];      // delta * y_h
-        const double Yx[3][3] = {{0, -y2, y1}, {y2, 0, -y0}, {-y1, y0, 0}};
-        for (int t = tid; t < 8 * 21; t += nt) {
-          const int v = t / 21, q = t % 21, e = v / 4;
-          const double ge = R[Q_GAM + e];
-          if (q < 18) {
-            const int a_ = (q % 9) / 3, b_ = q % 3;
-            const double val = ge * Yx[a_][b_];
-            if (q < 9) sm.M[(32 + IP + b_) * LDM + 3 * v + a_] += -val;
-            else sm.M[(32 + (e ? IPR : IPL) + b_) * LDM + 3 * v + a_] += val;
-          } else {
-            const int a_ = q - 18;
-            const double dx_ = R[Q_DR + 2 * v], dy_ = R[Q_DR + 2 * v + 1];
-            // y x (R'c) with R'c = (dx_, dy_, 0)
-            const double cr[3] = {-y2 * dy_, y2 * dx_, y0 * dy_ - y1 * dx_};
-            sm.M[(32 + (e ? IPSR : IPSL)) * LDM + 3 * v + a_] += ge * cr[a_];
-          }
-        }
-      }
-      par.sync();
+      assemble_stage(i, reg);
+      const double* R = sm.rec - Q_D;
       // W = P [B A]  (28 x 60);  tv = p + P d
       for (int t = tid; t < NX * NZ; t += nt) {
         const int r = t / NZ, j = t % NZ;
@@ -524,53 +564,60 @@ struct Solver {
       }
       par.sync();
       // M += [B A]' W (lower triangle), gradient row += [B A]' tv
-      for (int t = tid; t < MROWS * NZ; t += nt) {
+      for (int t = tid; t < (NZ + 1) * NZ; t += nt) {
         const int a_ = t / NZ, b_ = t % NZ;
         if (a_ < NZ) {
           if (b_ > a_) continue;
           double s = 0.0;
           for (int q = 0; q < 4; ++q) { const int rr = ba_row(a_, q); if (rr >= 0) s += sm.bav[4 * a_ + q] * sm.W[rr * NZ + b_]; }
-          sm.M[a_ * LDM + b_] += s;
+          sm.M[mz(a_) * LDM + mz(b_)] += s;
         } else {
           double s = 0.0;
           for (int q = 0; q < 4; ++q) { const int rr = ba_row(b_, q); if (rr >= 0) s += sm.bav[4 * b_ + q] * sm.tv[rr]; }
-          sm.M[NZ * LDM + b_] += s;
+          sm.M[GR * LDM + mz(b_)] += s;
         }
       }
       par.sync();
-      // partial Cholesky of the input block (right-looking), gradient row carried along
-      for (int k = 0; k < NU; ++k) {
+      // partial LDL' of the [u ; w] block (right-looking; D = +1 for inputs, -1 for the explicit multipliers),
+      // gradient row carried along
+      for (int k = 0; k < NA; ++k) {
         const double piv = sm.M[k * LDM + k];
-        if (!(piv > 1e-14)) return false;                 // uniform: every thread reads the same value
-        const double inv = 1.0 / sqrt(piv);
+        const double sgn = (k < NU) ? 1.0 : -1.0;
+#ifdef CMPC_TRACE
+        if (cmpc_trace_on && !(sgn * piv > (k < NU ? 1e-14 : 0.0))) printf("   pivot fail stage %d k %d piv %.3e reg %.1e\n", i, k, piv, reg);
+#endif
+        // inputs need a positive pivot; an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
+        if (!(sgn * piv > (k < NU ? 1e-14 : 0.0))) return false;           // uniform: every thread reads the same value
+        const double inv = 1.0 / sqrt(sgn * piv);
         par.sync();
-        for (int r = k + tid; r < MROWS; r += nt) sm.M[r * LDM + k] *= inv;      // M[k][k] becomes sqrt(piv)
+        for (int r = k + tid; r < MROWS; r += nt) sm.M[r * LDM + k] *= inv;    // M[k][k] becomes sgn * sqrt|piv|
         par.sync();
-        const int nrem = MROWS - (k + 1), ncol = NZ - (k + 1);
+        const int nrem = MROWS - (k + 1), ncol = NZA - (k + 1);
         for (int t = tid; t < nrem * ncol; t += nt) {
           const int r = k + 1 + t / ncol, cc = k + 1 + t % ncol;
           if (cc > r) continue;
-          sm.M[r * LDM + cc] -= sm.M[r * LDM + k] * sm.M[cc * LDM + k];
+          sm.M[r * LDM + cc] -= sgn * sm.M[r * LDM + k] * sm.M[cc * LDM + k];
         }
         par.sync();
       }
       // stream factors out; load P, p for the next stage
-      for (int t = tid; t < NU * NU; t += nt) { const int r = t / NU, cc = t % NU; if (cc <= r) fac[F_L + tri(r, cc)] = sm.M[r * LDM + cc]; }
-      for (int t = tid; t < NX * NU; t += nt) { const int r = t / NU, cc = t % NU; fac[F_LS + t] = sm.M[(32 + r) * LDM + cc]; }
-      for (int t = tid; t < NU; t += nt) fac[F_LM + t] = sm.M[NZ * LDM + t];
+      for (int t = tid; t < NA * NA; t += nt) { const int r = t / NA, cc = t % NA; if (cc <= r) fac[F_L + tri(r, cc)] = sm.M[r * LDM + cc]; }
+      for (int t = tid; t < NX * NA; t += nt) { const int r = t / NA, cc = t % NA; fac[F_LS + t] = sm.M[(XO + r) * LDM + cc]; }
+      for (int t = tid; t < NA; t += nt) fac[F_LM + t] = sm.M[GR * LDM + t];
       for (int t = tid; t < NX * NX; t += nt) {
         const int r = t / NX, cc = t % NX;
-        const double v = (cc <= r) ? sm.M[(32 + r) * LDM + 32 + cc] : sm.M[(32 + cc) * LDM + 32 + r];
+        const double v = (cc <= r) ? sm.M[(XO + r) * LDM + XO + cc] : sm.M[(XO + cc) * LDM + XO + r];
         sm.P[t] = v;
         if (cc <= r) fac[F_P + tri(r, cc)] = v;
       }
-      for (int t = tid; t < NX; t += nt) { const double v = sm.M[NZ * LDM + 32 + t]; sm.pv[t] = v; fac[F_PV + t] = v; }
+      for (int t = tid; t < NX; t += nt) { const double v = sm.M[GR * LDM + XO + t]; sm.pv[t] = v; fac[F_PV + t] = v; }
       par.sync();
     }
     return true;
   }
 
-  // ---- forward sweep: Newton step (DX, DU), full-step costates YN, slack steps DS.
+  // ---- forward sweep: Newton step (DX, DU), new multipliers of the explicit rows (DW), full-step costates YN.
+  // With M_aa = L D L', L_S = M_xa L^-T D^-1, l_m = D^-1 L^-1 m_a:  L' z = -(l_m + L_S' dx),  z = [du ; w].
   CMPC_HD void forward(double reg) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
     for (int t = tid; t < NX; t += nt) { sm.dxs[t] = 0.0; w.DX[t] = 0.0; }
@@ -579,11 +626,10 @@ struct Solver {
       const double* fac = w.FAC + (size_t)i * FACSZ;
       const double* rec = w.REC + (size_t)i * RECSZ;
       for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
-      // L into M[0:32][0:32] (lower), zs = l_m + L_S' dx
-      for (int t = tid; t < NU * NU; t += nt) { const int r = t / NU, cc = t % NU; if (cc <= r) sm.M[r * LDM + cc] = fac[F_L + tri(r, cc)]; }
-      for (int cidx = tid; cidx < NU; cidx += nt) {
+      for (int t = tid; t < NA * NA; t += nt) { const int r = t / NA, cc = t % NA; if (cc <= r) sm.M[r * LDM + cc] = fac[F_L + tri(r, cc)]; }
+      for (int cidx = tid; cidx < NA; cidx += nt) {
         double s = fac[F_LM + cidx];
-        for (int r = 0; r < NX; ++r) s += fac[F_LS + r * NU + cidx] * sm.dxs[r];
+        for (int r = 0; r < NX; ++r) s += fac[F_LS + r * NA + cidx] * sm.dxs[r];
         sm.zs[cidx] = -s;
       }
       // costate of stage i (full step): y_i = p_i + P_i dx_i
@@ -594,29 +640,29 @@ struct Solver {
       }
       for (int t = tid; t < NX; t += nt) sm.dxn[t] = rec[Q_D + t];
       par.sync();
-      // back substitution L' du = zs (column oriented)
-      for (int k = NU - 1; k >= 0; --k) {
-        const double duk = sm.zs[k] / sm.M[k * LDM + k];
+      // back substitution L' z = zs (column oriented)
+      for (int k = NA - 1; k >= 0; --k) {
+        const double zk = sm.zs[k] / sm.M[k * LDM + k];
         par.sync();
-        if (tid == 0) sm.zs[k] = duk;
-        for (int j = tid; j < k; j += nt) sm.zs[j] -= sm.M[k * LDM + j] * duk;
+        if (tid == 0) sm.zs[k] = zk;
+        for (int j = tid; j < k; j += nt) sm.zs[j] -= sm.M[k * LDM + j] * zk;
         par.sync();
       }
       for (int t = tid; t < NU; t += nt) w.DU[i * NU + t] = sm.zs[t];
-      // dx_{i+1} = d + A dx + B du   (row-parallel over the structural pattern: gather form)
+      for (int t = tid; t < NW; t += nt) w.DW[i * NW + t] = sm.zs[NU + t];
+      // dx_{i+1} = d + A dx + B du   (gather over the structural pattern)
       for (int r = tid; r < NX; r += nt) {
         double s = sm.dxn[r];
         for (int j = 0; j < NZ; ++j)
           for (int q = 0; q < 4; ++q)
-            if (ba_row(j, q) == r) s += sm.bav[4 * j + q] * (j < 32 ? sm.zs[j] : sm.dxs[j - 32]);
+            if (ba_row(j, q) == r) s += sm.bav[4 * j + q] * (j < NU ? sm.zs[j] : sm.dxs[j - NU]);
         sm.dxn[r] = s;
       }
       par.sync();
       for (int t = tid; t < NX; t += nt) { sm.dxs[t] = sm.dxn[t]; w.DX[(i + 1) * NX + t] = sm.dxn[t]; }
       par.sync();
     }
-    // terminal costate: y_N = p_N + P_N dx_N  (P_N diagonal)
-    {
+    {   // terminal costate: y_N = p_N + P_N dx_N  (P_N diagonal)
       const double* rec = w.REC + (size_t)N * RECSZ;
       for (int r = tid; r < NX; r += nt)
         w.YN[N * NX + r] = rec[Q_GC + 32 + r] + mu * rec[Q_M1 + 32 + r] + rec[Q_M2 + 32 + r]
@@ -674,7 +720,12 @@ struct Solver {
       stage_ineq(c, in, i, mask, x_, u_, xp, g);
       for (int r = 0; r < NR; ++r) {
         if (!(mask & (1ull << r))) { ds[r] = 0.0; continue; }
-        const double dsr = -(g[r] - c.relax + s[r]) - jd[r];
+        double dsr = -(g[r] - c.relax + s[r]) - jd[r];
+        if (r == R_LYAP || r == R_HW) {
+          // explicit rows: the solve returned the new multiplier w; ds follows from s dlam + lam ds = mu - s lam
+          const double dlw = w.DW[i * NW + (r == R_HW ? 1 : 0)] - lam[r];
+          dsr = mu / lam[r] - s[r] - s[r] / lam[r] * dlw;
+        }
         ds[r] = dsr;
         const double dl = -lam[r] + mu / s[r] - lam[r] / s[r] * dsr;
         if (dsr < 0.0) { const double a = -tau * s[r] / dsr; ap = a < ap ? a : ap; }
@@ -723,8 +774,21 @@ struct Solver {
     par.sync();
   }
 
-  // ---- the interior-point loop
+  // ---- warm-started solve with a cold retry: an interior-point method started next to the boundary of a
+  // changed active set can jam; a failed warm solve is repeated once from the solver's own cold start.
   CMPC_HD void run(int warm, Stats* st) {
+    run_once(warm, st);
+    if (warm != 0 && st->status != ST_CONVERGED && st->status != ST_INFEASIBLE_X0) {
+      const int it0 = st->iters;
+      par.sync();
+      mu = 0; reg_last = 0;
+      run_once(0, st);
+      st->iters += it0;
+    }
+  }
+
+  // ---- the interior-point loop
+  CMPC_HD void run_once(int warm, Stats* st) {
     const int N = c.N;
     double pviol;
     if (par.tid() == 0) { build_masks(c, in, sm.mask, &pviol); sm.red[0] = pviol; }
@@ -805,6 +869,10 @@ struct Solver {
       }
       apply_step(alpha, a_d);
       eval(ev);
+#ifdef CMPC_TRACE
+      if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",
+                               it, ev[5], ev[0], ev[1], ev[2], ev[3], mu, reg, a_p, a_d, alpha, (int)accepted);
+#endif
     }
     // final report: reference cost (no eps_reg term) and max unrelaxed violation incl. dynamics defects
     double tr[5];

@@ -25,6 +25,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 import scipy.sparse as sps
+import scipy.linalg as sla
 import scipy.sparse.linalg as spla
 
 from .spec import NG, NP, NU, NV, NX, PARAM_NAMES, block_functions
@@ -86,7 +87,8 @@ class Options:
     tau_min: float = 0.99
     bound_push: float = 1e-2
     verbose: bool = False
-    linesearch: str = "filter"   # "filter" | "none"
+    linesearch: str = "relaxed"  # "filter" | "relaxed" | "none"
+    inertia: bool = True          # exact inertia from a dense LDL' (slow, robust) vs curvature test on a sparse LU
 
     @staticmethod
     def oracle_T():
@@ -298,19 +300,44 @@ def solve(prob: Problem, w0: np.ndarray = None, opts: Options = None) -> Result:
         attempt = 0
         while True:
             K = sps.bmat([[Hbar + dw_reg * sps.identity(n), Jc.T], [Jc, None]], format="csc")
-            try:
-                lu = spla.splu(K)
+            ok = False
+            if opts.inertia:
+                # inertia of the KKT matrix from a dense Bunch-Kaufman LDL' (IPOPT sec. 3.1 asks for
+                # exactly n positive and m_eq negative eigenvalues)
+                Kd = K.toarray()
+                lu_, d_, perm_ = sla.ldl(Kd, lower=True)
+                nneg = 0
+                k_ = 0
+                nd = d_.shape[0]
+                while k_ < nd:
+                    if k_ + 1 < nd and d_[k_ + 1, k_] != 0.0:
+                        ev = np.linalg.eigvalsh(d_[k_:k_ + 2, k_:k_ + 2]); nneg += int((ev < 0).sum()); k_ += 2
+                    else:
+                        nneg += int(d_[k_, k_] < 0); k_ += 1
                 nfact += 1
-                sol = lu.solve(np.concatenate([rhs_w, -c]))
-                ok = np.all(np.isfinite(sol))
-            except RuntimeError:
-                ok = False
-            if ok:
-                dw = sol[:n]
-                dy = sol[n:]
-                curv = dw @ (Hbar @ dw) + dw_reg * (dw @ dw)
-                if curv >= 1e-12 * (dw @ dw) or (dw @ dw) == 0.0:
-                    break
+                if nneg == me:
+                    sol = np.linalg.solve(Kd, np.concatenate([rhs_w, -c]))
+                    # one step of iterative refinement
+                    res_ = np.concatenate([rhs_w, -c]) - Kd @ sol
+                    sol = sol + np.linalg.solve(Kd, res_)
+                    ok = bool(np.all(np.isfinite(sol)))
+                    if ok:
+                        dw = sol[:n]; dy = sol[n:]
+                        break
+            else:
+                try:
+                    lu = spla.splu(K)
+                    nfact += 1
+                    sol = lu.solve(np.concatenate([rhs_w, -c]))
+                    ok = bool(np.all(np.isfinite(sol)))
+                except RuntimeError:
+                    ok = False
+                if ok:
+                    dw = sol[:n]
+                    dy = sol[n:]
+                    curv = dw @ (Hbar @ dw) + dw_reg * (dw @ dw)
+                    if curv >= 1e-12 * (dw @ dw) or (dw @ dw) == 0.0:
+                        break
             # regularise (sec. 3.1): first 1e-4 (or last/3), then x100 / x8
             if dw_reg == 0.0:
                 dw_reg = 1e-4 if dw_last == 0.0 else max(1e-20, dw_last / 3.0)

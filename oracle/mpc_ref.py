@@ -92,18 +92,23 @@ class centroidal_mpc:  # noqa: N801  (reference class name)
         self.update_swing_trj = 0
 
 
-def surrogate_walk(mpc, initial, t0, t1, mass, push=True, record=None, verbose=False):
+def surrogate_walk(mpc, initial, t0, t1, mass, push=True, record=None, verbose=False, hw_trace=None):
     """Closed loop with the centroidal model itself as the plant.
 
-    x_{t+1} := the MPC's own x_1; theta_hat is fed back by the MPC object as in :485; the
-    reference's lateral push (3 N on two bodies for 800 < t < 900, `code/simulation.py:195-198`)
-    enters as dv_y += 6/m * 0.01 per tick.
+    CoM position / velocity at t+1 := the MPC's own x_1; theta_hat is fed back by the MPC object as in
+    :485; the reference's lateral push (3 N on two bodies for 800 < t < 900,
+    `code/simulation.py:195-198`) enters as dv_y += 6/m * 0.01 per tick.  The measured whole-body
+    angular momentum cannot come from the centroidal model (row :224 would pin it to ~0 for ever and
+    the single-support ticks become infeasible); `hw_trace[t]` replays the reference's own recorded
+    measurement (`original_code/cuhw.txt`) instead.
     """
     cur = {"com": {"pos": np.array(initial["com"]["pos"], float), "vel": np.array(initial["com"]["vel"], float)},
            "hw": {"val": np.array(initial["hw"]["val"], float)},
            "lfoot": {"pos": np.array(initial["lfoot"]["pos"], float)},
            "rfoot": {"pos": np.array(initial["rfoot"]["pos"], float)}}
     traj = []
+    if hw_trace is not None:
+        cur["hw"]["val"] = np.array(hw_trace[min(t0, len(hw_trace) - 1)], float)
     for t in range(t0, t1):
         ms, contact = mpc.solve(cur, t)
         if record is not None:
@@ -113,7 +118,7 @@ def surrogate_walk(mpc, initial, t0, t1, mass, push=True, record=None, verbose=F
         cur["com"]["vel"] = ms["com"]["vel"].copy()
         if push and 800 < t < 900:
             cur["com"]["vel"][1] += 6.0 / mass * 0.01
-        cur["hw"]["val"] = ms["hw"]["val"].copy()
+        cur["hw"]["val"] = ms["hw"]["val"].copy() if hw_trace is None else np.array(hw_trace[min(t + 1, len(hw_trace) - 1)], float)
         cur["lfoot"]["pos"][2] = float(ms["ang_contact_left"]["val"])
         cur["rfoot"]["pos"][2] = float(ms["ang_contact_right"]["val"])
         if ms["counter"]["val"] == 1:

@@ -63,6 +63,7 @@ def load_walk(path: str = None):
     params["eta"] = float(np.sqrt(params["g"] / params["h"]))
     initial = {"lfoot": {"pos": np.array(data["lfoot0"], float)}, "rfoot": {"pos": np.array(data["rfoot0"], float)},
                "com": {"pos": np.array([0.0, 0.0, 0.72]), "vel": np.zeros(3)}, "hw": {"val": np.zeros(3)}}
+    initial["hw_meas"] = np.array(data["hw_meas"], float) if "hw_meas" in data.files else None
     return planner, com_ref, params, initial
 
 

@@ -12,6 +12,9 @@ What is taken from the reference *by importing it* (stub `casadi`/`matplotlib` m
 What is restated: `quintic_spline` (`functions.py:129-157`) is an equality-only feasibility NLP
 (`f = 0`) solved by IPOPT from p = 0; one Newton step from 0 on a full-row-rank linear system lands
 on the minimum-norm solution, so `numpy.linalg.lstsq` is used (ASSUMPTION, nothing pins it).
+The measured whole-body angular momentum of the reference's own N=10 walk (`original_code/cuhw.txt`,
+1962 rows; `original_code/plot.py:14-18` reads it) is stored as `hw_meas`: it is the only recorded
+closed-loop signal in the reference tree and is replayed as the "measured" h_w of the surrogate plant.
 Inputs that need DART (initial foot poses, robot mass) are the literals recovered from
 `code/Debug/contact_trj_from_centroidal_MPC` line 1 and the URDF mass sum.
 """
@@ -98,8 +101,9 @@ def main():
     plan_ss = np.array([s['ss_duration'] for s in planner.plan])
     plan_ds = np.array([s['ds_duration'] for s in planner.plan])
     plan_foot = np.array([0 if s['foot_id'] == 'lfoot' else 1 for s in planner.plan])
+    hw_meas = np.loadtxt("/root/reference/original_code/cuhw.txt")
     np.savez_compressed(
-        OUT, plan_pos=plan_pos, plan_ang=plan_ang, plan_ss=plan_ss, plan_ds=plan_ds, plan_foot=plan_foot,
+        OUT, hw_meas=hw_meas, plan_pos=plan_pos, plan_ang=plan_ang, plan_ss=plan_ss, plan_ds=plan_ds, plan_foot=plan_foot,
         contact_left=planner.position_contacts_ref['contact_left'],
         contact_right=planner.position_contacts_ref['contact_right'],
         knot_x=np.array(knot_x), knot_y=np.array(knot_y), seq_x=np.array(seq_x), seq_y=np.array(seq_y),

@@ -2,6 +2,8 @@
 // Compiles the product's solver core (csrc/cmpc_solver.h) with g++ and a serial execution policy so the
 // algorithm can be debugged in a container without a GPU.  The product path is the CUDA build in
 // csrc/cmpc_kernels.cu and fails loudly when that extension is missing; nothing here is a fallback.
+#define CMPC_TRACE 1
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -17,9 +19,36 @@ struct ParSerial {
 
 extern "C" {
 
+void hostsim_trace(int on) { cmpc::cmpc_trace_on = on; }
+
 int hostsim_work_doubles(int N) { return (int)work_doubles(N); }
 
 // cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm} (NaN = keep default)
+// Debug: stage-i Lagrangian gradient (60) and assembled stage block M (60x60, lower) at the iterate stored in
+// `work` (X, U, Y, S, LAM as laid out by carve_work).  Used by tests to check the analytic Hessian by finite
+// differences of the analytic gradient.
+int hostsim_stage_debug(int N, const double* x0, const double* com_ref, const double* foot_ref, const double* gamma,
+                        double mass, double k1, double* work, int i, double mu, double* grad_out, double* M_out) {
+  Config c = default_config(N);
+  Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
+  Work w = carve_work(work, N);
+  Smem* sm = new Smem();
+  ParSerial par;
+  Solver<ParSerial> sol(c, in, w, *sm, par);
+  double pv; build_masks(c, in, sm->mask, &pv);
+  sol.mu = mu;
+  double acc[8];
+  stage_derivs(c, in, w, i, sm->mask[i], mu, acc);
+  for (int j = 0; j < 60; ++j) grad_out[j] = cmpc_dbg_rd[j];
+  sol.assemble_stage(i, 0.0);
+  for (int r = 0; r < 60; ++r) for (int cc = 0; cc < 60; ++cc) {
+    const int a = r < NU ? r : r + NW, b = cc < NU ? cc : cc + NW;
+    M_out[r * 60 + cc] = sm->M[(a >= b ? a : b) * LDM + (a >= b ? b : a)];
+  }
+  delete sm;
+  return 0;
+}
+
 int hostsim_solve(int N, const double* x0, const double* com_ref, const double* foot_ref, const double* gamma,
                   double mass, double k1, const double* cfg_over, int warm, double* work, double* stats_out) {
   Config c = default_config(N);

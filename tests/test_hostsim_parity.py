@@ -1,0 +1,77 @@
+"""CPU check of the product's solver CORE (csrc/cmpc_solver.h, cmpc_model.h) compiled by g++ with a serial
+execution policy (tests/hostsim -- a test aid, never a product path) against the oracle's golden vectors.
+Catches errors in the analytic derivatives / Riccati algebra here, where there is no GPU; the CUDA build of the
+same source is checked by tests/test_gpu_parity.py on the B200."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import hostsim
+from parity import COST_TOL, U0_TOL, VIOL_TOL, X1_TOL, cost_err, u0_err
+
+
+class P:
+    pass
+
+
+def problem(g, k, N):
+    p = P()
+    p.N = N
+    p.x0 = g["x0"][k]
+    p.com_ref = g["com_ref"][k].T
+    f = g["foot_ref"][k]
+    p.pl_ref, p.pr_ref, p.al_ref, p.ar_ref = f[:, 0:3].T, f[:, 3:6].T, f[:, 6], f[:, 7]
+    p.gl, p.gr = g["gamma"][k][:, 0], g["gamma"][k][:, 1]
+    p.mass, p.k1, p.eps_reg, p.w_rate = float(g["mass"]), float(g["k1"]), 1e-9, 1.0
+    return p
+
+
+@pytest.mark.parametrize("N", [10, 20])
+def test_core_matches_oracle_golden(golden, N):
+    g = golden[N]
+    ks = range(len(g["ticks"])) if N == 10 else range(0, len(g["ticks"]), 3)
+    for k in ks:
+        if g["status"][k] != 0:
+            continue
+        r = hostsim.solve(problem(g, k, N))
+        assert r["status"] == 0, (N, int(g["ticks"][k]), r["status"])
+        assert cost_err(r["cost"], g["cost"][k]) <= COST_TOL
+        assert r["viol"] <= VIOL_TOL
+        assert np.abs(r["X"][:12, 1] - g["X"][k, 1, :12]).max() <= X1_TOL
+        assert u0_err(r["U"][:, 0], g["U"][k, 0], g["x0"][k], g["gamma"][k, 0])[0] <= U0_TOL
+
+
+def test_analytic_stage_hessian_against_finite_differences(golden):
+    """Hessian of the stage Lagrangian assembled by the backward pass == central differences of the analytic
+    stage gradient (costates and multipliers random, slacks huge so the barrier part vanishes)."""
+    g = golden[10]
+    N, NX, NU, NR = 10, 28, 32, 56
+    k = list(g["ticks"]).index(262)                    # a landing inside the horizon: both feet, swing, yaw terms
+    prob = problem(g, k, N)
+    r = hostsim.solve(prob, max_iter=8)
+    L = hostsim.lib()
+    x0, com, foot, gam = hostsim.pack(prob)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    oU = (N + 1) * NX; oY = oU + N * NU; oS = oY + (N + 1) * NX; oL = oS + (N + 1) * NR
+    rng = np.random.default_rng(1)
+    wk = r["work"].copy()
+    wk[oS:oL] = 1e30
+    wk[oY:oS] = rng.normal(size=(N + 1) * NX) * 50
+
+    def dbg(work, i):
+        gr, M = np.zeros(60), np.zeros(3600)
+        L.hostsim_stage_debug(ctypes.c_int(N), dp(x0), dp(com), dp(foot), dp(gam), ctypes.c_double(prob.mass),
+                              ctypes.c_double(prob.k1), dp(work), ctypes.c_int(i), ctypes.c_double(1e-3), dp(gr), dp(M))
+        return gr, M.reshape(60, 60)
+
+    for i in (1, 4, 8):
+        _, M = dbg(wk, i)
+        H = np.zeros((60, 60))
+        for j in range(60):
+            h = 1e-6
+            wp, wm = wk.copy(), wk.copy()
+            idx = oU + i * NU + j if j < 32 else i * NX + (j - 32)
+            wp[idx] += h; wm[idx] -= h
+            H[:, j] = (dbg(wp, i)[0] - dbg(wm, i)[0]) / (2 * h)
+        assert np.abs(H - M).max() <= 1e-5 * max(1.0, np.abs(M).max()), i
