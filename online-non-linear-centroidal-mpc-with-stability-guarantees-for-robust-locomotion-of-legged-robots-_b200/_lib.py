@@ -37,19 +37,21 @@ def library_path() -> str:
     return _SO
 
 
-def nvcc_command(out: str = _SO):
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+def nvcc_command(out: str = _SO, extra=()):
+    return ["nvcc", *extra, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "--expt-relaxed-constexpr", "-diag-suppress", "170", "-Xptxas", "-v", "-shared", "-Xcompiler", "-fPIC",
             "-o", out, os.path.join(_HERE, "csrc", "cmpc_kernels.cu")]
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, profile: bool = None) -> str:
     """Compile csrc/cmpc_kernels.cu for sm_100a into libcmpc_b200.so (in-tree)."""
     srcs = [os.path.join(_HERE, "csrc", f) for f in ("cmpc_kernels.cu", "cmpc_solver.h", "cmpc_model.h")]
     srcs.append(os.path.join(_ROOT, "include", "cmpc.h"))
     if not force and os.path.exists(_SO) and all(os.path.getmtime(s) <= os.path.getmtime(_SO) for s in srcs):
         return _SO
-    res = subprocess.run(nvcc_command(), capture_output=True, text=True)
+    if profile is None:
+        profile = os.environ.get("CMPC_PROFILE", "0") == "1"
+    res = subprocess.run(nvcc_command(extra=("-DCMPC_PROFILE",) if profile else ()), capture_output=True, text=True)
     if verbose or res.returncode:
         print(res.stdout + res.stderr)
     if res.returncode:
@@ -83,6 +85,7 @@ def load():
     L.cmpc_warm_restore.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
     L.cmpc_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                   ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)]
+    L.cmpc_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
     L.cmpc_footprint.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
     L.cmpc_measure_fp64_peak.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
     _lib = L
@@ -91,7 +94,7 @@ def load():
 
 EXPORTS = ["cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_last_error", "cmpc_version", "cmpc_solve_device",
            "cmpc_solve_host", "cmpc_get_trajectory", "cmpc_set_warm", "cmpc_reset_warm", "cmpc_warm_save", "cmpc_warm_restore", "cmpc_last_stats",
-           "cmpc_footprint", "cmpc_measure_fp64_peak"]
+           "cmpc_footprint", "cmpc_phase_cycles", "cmpc_measure_fp64_peak"]
 
 
 def _check(L, rc, what):
@@ -219,6 +222,12 @@ class BatchSolver:
         _check(self._L, self._L.cmpc_last_stats(self._h, ctypes.byref(it), ctypes.byref(nf), ctypes.byref(nr),
                                                 ctypes.byref(ms), ctypes.byref(nl)), "cmpc_last_stats")
         return {"iters": it.value, "nfact": nf.value, "nreg": nr.value, "kernel_ms": ms.value, "launches": nl.value}
+
+    def phase_cycles(self) -> dict:
+        arr = (ctypes.c_uint64 * 9)()
+        _check(self._L, self._L.cmpc_phase_cycles(self._h, arr), "cmpc_phase_cycles")
+        names = ["eval", "assemble", "pba", "factor", "store", "forward", "slack", "trial", "apply"]
+        return dict(zip(names, [int(v) for v in arr]))
 
     def footprint(self) -> dict:
         a, b = ctypes.c_size_t(), ctypes.c_size_t()

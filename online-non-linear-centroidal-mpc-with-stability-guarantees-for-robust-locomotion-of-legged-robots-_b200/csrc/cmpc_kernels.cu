@@ -17,7 +17,7 @@ using namespace cmpc;
 #define CMPC_THREADS 128     // threads per instance (CTA size)
 #endif
 #ifndef CMPC_MIN_CTAS
-#define CMPC_MIN_CTAS 4      // resident CTAs per SM the register allocation is sized for
+#define CMPC_MIN_CTAS 3      // resident CTAs per SM the register allocation is sized for (shared memory allows 3)
 #endif
 
 namespace {
@@ -36,12 +36,19 @@ struct ParCta {
   __device__ int tid() const { return (int)threadIdx.x; }
   __device__ int nt() const { return (int)blockDim.x; }
   __device__ void sync() const { __syncthreads(); }
+  __device__ int lane() const { return (int)(threadIdx.x & 31); }
+  __device__ int warp() const { return (int)(threadIdx.x >> 5); }
+  __device__ int nwarps() const { return (int)(blockDim.x >> 5); }
+  __device__ int lanes() const { return 32; }
+  __device__ void sync_warp() const { __syncwarp(); }
+  static constexpr int TPT = 2;      // 4x4 register tiles per thread: 136 tiles over 128 threads
 };
 
 struct Outputs {
   double *x1, *u0, *xN, *cost, *viol;
   int32_t *status, *iters;
   int32_t* counters;   // [B][2] nfact, nreg
+  unsigned long long* prof;   // [PF_COUNT] phase cycles summed over CTAs (only with -DCMPC_PROFILE)
 };
 
 __global__ void __launch_bounds__(CMPC_THREADS, CMPC_MIN_CTAS)
@@ -52,6 +59,9 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int N = c.N;
+#ifdef CMPC_PROFILE
+  if (threadIdx.x == 0) for (int k = 0; k < PF_COUNT; ++k) sm.prof[k] = 0;
+#endif
   for (int b = blockIdx.x; b < batch; b += gridDim.x) {
     Instance in;
     in.x0 = x0 + (size_t)NXP * b;
@@ -79,6 +89,9 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
     }
     __syncthreads();
   }
+#ifdef CMPC_PROFILE
+  if (threadIdx.x == 0 && out.prof) for (int k = 0; k < PF_COUNT; ++k) atomicAdd(&out.prof[k], (unsigned long long)sm.prof[k]);
+#endif
 }
 
 // gather / scatter between the 28-wide internal state layout and the 20-wide reference layout
@@ -125,6 +138,7 @@ struct cmpc_handle {
   double* d_in; double* d_out; int32_t* d_iout;
   double* h_in; double* h_out; int32_t* h_iout;
   int32_t* d_counters; int32_t* h_counters;
+  unsigned long long* d_prof;
   size_t in_doubles, out_doubles;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
@@ -170,7 +184,7 @@ static Config to_internal(const cmpc_config* u) {
 int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, cmpc_handle** out) {
   if (!cfg || !out || batch_capacity < 1) return fail(-1, "cmpc_create: bad arguments");
   if (cfg->N < 1 || cfg->N > NMAX) return fail(-1, "cmpc_create: horizon must satisfy 1 <= N <= 64");
-  if (cfg->threads < 32 || cfg->threads > CMPC_THREADS || cfg->threads % 32) return fail(-1, "cmpc_create: threads must be 32..128, multiple of 32");
+  if (cfg->threads != CMPC_THREADS) return fail(-1, "cmpc_create: threads must be 128 (register-tile mapping of the stage factorisation)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) return fail(-3, "cmpc_create: no CUDA device (this library has no CPU path)", e);
@@ -195,6 +209,9 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
   CK(cudaMallocHost(&h->h_out, B * h->out_doubles * sizeof(double)), "cudaMallocHost(h_out)");
   CK(cudaMallocHost(&h->h_iout, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_iout)");
   CK(cudaMallocHost(&h->h_counters, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_counters)");
+#ifdef CMPC_PROFILE
+  CK(cudaMalloc(&h->d_prof, PF_COUNT * sizeof(unsigned long long)), "cudaMalloc(d_prof)");
+#endif
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CK(cudaEventCreate(&h->ev0), "cudaEventCreate");
   CK(cudaEventCreate(&h->ev1), "cudaEventCreate");
@@ -227,7 +244,8 @@ int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const dou
   if (warm_mode != CMPC_COLD && h->warm_valid < batch) warm_mode = CMPC_COLD;     // nothing to warm-start from
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-  Outputs o{x1, u0, xN, cost, viol, status, iters, h->d_counters};
+  Outputs o{x1, u0, xN, cost, viol, status, iters, h->d_counters, h->d_prof};
+  if (h->d_prof) CK(cudaMemsetAsync(h->d_prof, 0, PF_COUNT * sizeof(unsigned long long), s), "memset prof");
   CK(cudaEventRecord(h->ev0, s), "cudaEventRecord");
   cmpc_solve_kernel<<<batch, h->threads, sizeof(Smem), s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1,
                                                             h->work, h->wstride, warm_mode, o);
@@ -357,6 +375,15 @@ int cmpc_last_stats(cmpc_handle* h, int64_t* iters, int64_t* nfact, int64_t* nre
   if (iters) *iters = nf - nr;
   if (kernel_ms) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1), "cudaEventElapsedTime"); *kernel_ms = ms; }
   if (launches) *launches = h->last_launches;
+  return 0;
+}
+
+/* Phase cycle counters of the last solve (all zeros unless built with -DCMPC_PROFILE): eval, assemble,
+ * P[B A] products, factorisation, factor store, forward sweep, slack steps, line-search trials, step. */
+int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out9) {
+  if (!h || !out9) return fail(-1, "cmpc_phase_cycles: bad arguments");
+  for (int k = 0; k < PF_COUNT; ++k) out9[k] = 0;
+  if (h->d_prof) { CK(cudaSetDevice(h->device), "cudaSetDevice"); CK(cudaMemcpy(out9, h->d_prof, PF_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost), "D2H prof"); }
   return 0;
 }
 

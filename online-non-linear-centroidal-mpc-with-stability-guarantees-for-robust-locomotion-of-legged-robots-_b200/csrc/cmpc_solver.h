@@ -29,13 +29,24 @@ constexpr int MROWS = NZA + 1;              // 62 variable rows + the gradient r
 constexpr int TRI_A = NA * (NA + 1) / 2;    // 595
 constexpr int TRI_X = NX * (NX + 1) / 2;    // 406
 // per-stage factor record streamed to global memory
-constexpr int F_L = 0, F_LS = F_L + TRI_A, F_LM = F_LS + NX * NA, F_P = F_LM + NA, F_PV = F_P + TRI_X;
-constexpr int FACSZ = F_PV + NX;            // 2015 doubles
+constexpr int F_K = 0, F_P = F_K + (NX + 1) * NA, F_PV = F_P + TRI_X;   // gains K (28 x 34) + k (34), cost-to-go P, p
+constexpr int FACSZ = F_PV + NX;            // 1420 doubles
+constexpr int NTILE = 16 * 17 / 2;          // 4 x 4 tiles of the padded 64 x 64 lower triangle
 // per-stage derivative record written by the eval pass
 constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
               Q_LG = 556, Q_LC = 568, Q_LSIG = 584, Q_HP = 585, Q_HLAM = 588, Q_HSIG = 589, Q_YH = 590,
               Q_GAM = 593, Q_GAMP = 595, Q_DR = 600, Q_LRG = 616, Q_LLAM = 617, Q_HRG = 618;
 constexpr int RECSZ = 620;
+
+// optional phase timers (cycles, thread 0 of each CTA): -DCMPC_PROFILE
+#if defined(CMPC_PROFILE) && defined(__CUDA_ARCH__)
+#define CMPC_TIC(sm) long long tic_ = clock64()
+#define CMPC_TOC(sm, k) do { if (threadIdx.x == 0) { long long now_ = clock64(); (sm).prof[k] += now_ - tic_; tic_ = now_; } } while (0)
+#else
+#define CMPC_TIC(sm) do {} while (0)
+#define CMPC_TOC(sm, k) do {} while (0)
+#endif
+enum { PF_EVAL = 0, PF_ASM, PF_PBA, PF_CHOL, PF_STORE, PF_FWD, PF_SLACK, PF_TRIAL, PF_APPLY, PF_COUNT };
 
 #ifdef CMPC_TRACE
 static int cmpc_trace_on = 0;
@@ -74,10 +85,15 @@ struct Smem {
   double bav[NZ * 4];        // sparse [B A] values of the current stage
   double rec[RECSZ - Q_D];   // rest of the current record (d, diag, friction, Lyapunov, ...)
   double dxs[NX], dxn[NX], zs[NA];
+  double colbuf[2 * 64];     // pivot column, double buffered
   double red[40];
   uint64_t mask[NMAX + 1];
   double acc[NMAX + 1][8];   // per-stage partial results of eval / trial passes
   int flag;
+  long long prof[PF_COUNT];
+  short csr_ptr[NX + 1];      // structural pattern of [B A] by rows (gather form)
+  unsigned char csr_idx[NZ * 4];
+  signed char barow[NZ * 4];  // ba_row(j, q) table
 };
 
 struct Stats { double cost, viol, kkt, mu; int iters, status, nfact, nreg; };
@@ -448,6 +464,7 @@ struct Solver {
       sm.M[(NU + 1) * LDM + NU + 1] = has_hw ? -1.0 / R[Q_HSIG] : -1.0;
       sm.M[GR * LDM + NU + 1] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
     }
+    par.sync();
     // friction barrier blocks (lower triangle)
     for (int t = tid; t < 48; t += nt) {
       const int v = t / 6, e6 = t % 6;
@@ -468,27 +485,29 @@ struct Solver {
       }
     }
     par.sync();
-    // Lyapunov row: lam * C (x) I_3 curvature over the 33 touched variables, and its gradient as row/column NU
-    for (int t = tid; t < 33 * 33 + 33; t += nt) {
-      if (t >= 33 * 33) {
-        const int ai = t - 33 * 33;
+    // Lyapunov row: lam * C (x) I_3 curvature over the 33 touched variables, and its gradient as row/column NU.
+    // Touched variable a (0..32): forces 0..23 (type F, scaled by gamma_e), then p, v, theta.
+    {
+      const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
+      for (int ai = wid; ai < 33; ai += nw) {
         int ma, ta, xa; double sa;
         if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
         else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
-        const double gv = sa * R[Q_LG + 3 * ta + xa];
-        if (ma < NU) sm.M[NU * LDM + ma] = gv; else sm.M[ma * LDM + NU] = gv;
-        continue;
+        if (lane == 0) {
+          const double gv = sa * R[Q_LG + 3 * ta + xa];
+          if (ma < NU) sm.M[NU * LDM + ma] = gv; else sm.M[ma * LDM + NU] = gv;
+        }
+        if (sa == 0.0) continue;
+        // same-axis partners only: bi = xa, xa + 3, ... (forces and states keep the axis in the low index)
+        for (int bq = lane; 3 * bq + xa <= ai; bq += nl) {
+          const int bi = 3 * bq + xa;
+          int mb, tb; double sb;
+          if (bi < 24) { mb = bi; tb = 3; sb = R[Q_GAM + bi / 12]; }
+          else { const int q = bi - 24; tb = q / 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xa; }
+          const double v = sa * sb * R[Q_LC + 4 * ta + tb];
+          if (ma >= mb) sm.M[ma * LDM + mb] += v; else sm.M[mb * LDM + ma] += v;
+        }
       }
-      const int ai = t / 33, bi = t % 33;
-      if (bi > ai) continue;
-      int ma, ta, xa; double sa; int mb, tb, xb; double sb;
-      if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
-      else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
-      if (bi < 24) { mb = bi; tb = 3; xb = bi % 3; sb = R[Q_GAM + bi / 12]; }
-      else { const int q = bi - 24; tb = q / 3; xb = q % 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xb; }
-      if (xa != xb) continue;
-      const double v = sa * sb * R[Q_LC + 4 * ta + tb];
-      if (ma >= mb) sm.M[ma * LDM + mb] += v; else sm.M[mb * LDM + ma] += v;
     }
     par.sync();
     // angular-momentum row (stage 0): curvature 2 lam Bh'Bh in the force block, gradient as row NU+1
@@ -535,27 +554,38 @@ struct Solver {
   }
 
   // ---- backward Riccati sweep.  Returns false if a pivot has the wrong sign (inputs > 0, multipliers < 0).
+  // Thread mapping: one warp per matrix row (rows dealt cyclically to the warps), lanes across the columns of the
+  // row: shared-memory accesses are conflict-free (row stride 63 doubles) and whole rows whose multiplier is zero
+  // -- the stage block is sparse: stance-foot inputs, swing-foot forces, previous-f_z states -- are skipped
+  // without divergence.
   CMPC_HD bool backward(double reg) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
     {   // terminal stage: P_N diagonal, p_N = modified gradient (x part)
       const double* rec = w.REC + (size_t)N * RECSZ;
-      for (int t = tid; t < NX * NX; t += nt) {
-        const int r = t / NX, cc = t % NX;
-        sm.P[t] = (r == cc) ? rec[Q_DIAG + 32 + r] + reg : 0.0;
+      for (int t = tid; t < NX * NX; t += nt) sm.P[t] = 0.0;
+      par.sync();
+      for (int t = tid; t < NX; t += nt) {
+        sm.P[t * NX + t] = rec[Q_DIAG + 32 + t] + reg;
+        sm.pv[t] = rec[Q_GC + 32 + t] + mu * rec[Q_M1 + 32 + t] + rec[Q_M2 + 32 + t];
       }
-      for (int t = tid; t < NX; t += nt) sm.pv[t] = rec[Q_GC + 32 + t] + mu * rec[Q_M1 + 32 + t] + rec[Q_M2 + 32 + t];
       par.sync();
     }
     for (int i = N - 1; i >= 0; --i) {
       double* fac = w.FAC + (size_t)i * FACSZ;
+      CMPC_TIC(sm);
       assemble_stage(i, reg);
+      CMPC_TOC(sm, PF_ASM);
       const double* R = sm.rec - Q_D;
-      // W = P [B A]  (28 x 60);  tv = p + P d
-      for (int t = tid; t < NX * NZ; t += nt) {
-        const int r = t / NZ, j = t % NZ;
-        double s = 0.0;
-        for (int q = 0; q < 4; ++q) { const int rr = ba_row(j, q); if (rr >= 0) s += sm.P[r * NX + rr] * sm.bav[4 * j + q]; }
-        sm.W[t] = s;
+      // W = P [B A]  (28 x 60): warp per row r, lanes over columns j;  tv = p + P d
+      for (int r = wid; r < NX; r += nw) {
+        const double* Pr = sm.P + r * NX;
+        for (int j = lane; j < NZ; j += nl) {
+          double s = 0.0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const int rr = sm.barow[4 * j + q]; if (rr >= 0) s += Pr[rr] * sm.bav[4 * j + q]; }
+          sm.W[r * NZ + j] = s;
+        }
       }
       for (int r = tid; r < NX; r += nt) {
         double s = sm.pv[r];
@@ -563,61 +593,159 @@ struct Solver {
         sm.tv[r] = s;
       }
       par.sync();
-      // M += [B A]' W (lower triangle), gradient row += [B A]' tv
-      for (int t = tid; t < (NZ + 1) * NZ; t += nt) {
-        const int a_ = t / NZ, b_ = t % NZ;
+      // M += [B A]' W (lower triangle), gradient row += [B A]' tv : warp per row a, lanes over b <= a
+      for (int a_ = wid; a_ <= NZ; a_ += nw) {
         if (a_ < NZ) {
-          if (b_ > a_) continue;
-          double s = 0.0;
-          for (int q = 0; q < 4; ++q) { const int rr = ba_row(a_, q); if (rr >= 0) s += sm.bav[4 * a_ + q] * sm.W[rr * NZ + b_]; }
-          sm.M[mz(a_) * LDM + mz(b_)] += s;
+          int rr[4]; double bv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { rr[q] = sm.barow[4 * a_ + q]; bv[q] = sm.bav[4 * a_ + q]; }
+          if (rr[0] < 0) continue;                               // structurally empty column (previous-f_z states)
+          double* Mr = sm.M + mz(a_) * LDM;
+          for (int b_ = lane; b_ <= a_; b_ += nl) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (rr[q] >= 0) s += bv[q] * sm.W[rr[q] * NZ + b_];
+            Mr[mz(b_)] += s;
+          }
         } else {
-          double s = 0.0;
-          for (int q = 0; q < 4; ++q) { const int rr = ba_row(b_, q); if (rr >= 0) s += sm.bav[4 * b_ + q] * sm.tv[rr]; }
-          sm.M[GR * LDM + mz(b_)] += s;
+          for (int b_ = lane; b_ < NZ; b_ += nl) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int r2 = sm.barow[4 * b_ + q]; if (r2 >= 0) s += sm.bav[4 * b_ + q] * sm.tv[r2]; }
+            sm.M[GR * LDM + mz(b_)] += s;
+          }
         }
       }
       par.sync();
-      // partial LDL' of the [u ; w] block (right-looking; D = +1 for inputs, -1 for the explicit multipliers),
-      // gradient row carried along
-      for (int k = 0; k < NA; ++k) {
-        const double piv = sm.M[k * LDM + k];
-        const double sgn = (k < NU) ? 1.0 : -1.0;
+      CMPC_TOC(sm, PF_PBA);
+      // ---- partial LDL' of the [u ; w] block, right-looking, matrix held in REGISTER tiles: the 64 x 64 (padded)
+      // lower triangle is cut into 4 x 4 tiles, one or two per thread; per pivot column the owners publish the
+      // column through a double-buffered shared vector (one barrier per column), every thread then updates its
+      // tile with 16 FMAs fed by 8 shared loads.  D = +1 for inputs, -1 for the explicit multipliers; the
+      // gradient row (row 62) is carried along.
+      {
+        double T[Par::TPT][16];
+        int ti_[Par::TPT], tj_[Par::TPT];
+#pragma unroll
+        for (int sl = 0; sl < Par::TPT; ++sl) {
+          const int tile = tid + sl * nt;
+          int ti = 0;
+          if (tile < NTILE) { while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti; }
+          ti_[sl] = tile < NTILE ? ti : -1;
+          tj_[sl] = tile < NTILE ? tile - ti * (ti + 1) / 2 : 0;
+          if (tile < NTILE) {
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+              for (int b_ = 0; b_ < 4; ++b_) {
+                const int r = 4 * ti + a_, cc = 4 * tj_[sl] + b_;
+                T[sl][4 * a_ + b_] = (r < MROWS && cc <= r && cc < NZA) ? sm.M[r * LDM + cc] : 0.0;
+              }
+          }
+        }
+        bool okp = true;
+        for (int tk = 0; tk < (NA + 3) / 4 && okp; ++tk) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {                          // kk static: tiles stay in registers
+            const int k = 4 * tk + kk;
+            if (k >= NA || !okp) break;
+            double* cb = sm.colbuf + (k & 1) * 64;
+#pragma unroll
+            for (int sl = 0; sl < Par::TPT; ++sl)
+              if (ti_[sl] >= 0 && tj_[sl] == tk) {
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_) cb[4 * ti_[sl] + a_] = T[sl][4 * a_ + kk];
+              }
+            par.sync();
+            const double piv = cb[k];
+            const double sgn = (k < NU) ? 1.0 : -1.0;
 #ifdef CMPC_TRACE
-        if (cmpc_trace_on && !(sgn * piv > (k < NU ? 1e-14 : 0.0))) printf("   pivot fail stage %d k %d piv %.3e reg %.1e\n", i, k, piv, reg);
+            if (cmpc_trace_on && !(sgn * piv > (k < NU ? 1e-14 : 0.0))) printf("   pivot fail stage %d k %d piv %.3e reg %.1e\n", i, k, piv, reg);
 #endif
-        // inputs need a positive pivot; an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
-        if (!(sgn * piv > (k < NU ? 1e-14 : 0.0))) return false;           // uniform: every thread reads the same value
-        const double inv = 1.0 / sqrt(sgn * piv);
+            // inputs need a positive pivot; an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
+            if (!(sgn * piv > (k < NU ? 1e-14 : 0.0))) { okp = false; break; }    // uniform: same value for every thread
+            const double inv = 1.0 / sqrt(sgn * piv);
+#pragma unroll
+            for (int sl = 0; sl < Par::TPT; ++sl) {
+              const int ti = ti_[sl], tj = tj_[sl];
+              if (ti < tk || tj < tk) continue;                       // (ti < 0 included) tile above / left of the pivot: final
+              double lr[4], lc[4];
+#pragma unroll
+              for (int a_ = 0; a_ < 4; ++a_) { lr[a_] = cb[4 * ti + a_] * inv; lc[a_] = cb[4 * tj + a_] * inv; }
+              if (tj == tk) {
+                // tile holds column k itself: entries left of / on column k need the index tests
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                  for (int b_ = 0; b_ < 4; ++b_) {
+                    const int r = 4 * ti + a_;
+                    if (b_ > kk) { if (r > k && 4 * tj + b_ <= r) T[sl][4 * a_ + b_] -= sgn * lr[a_] * lc[b_]; }
+                    else if (b_ == kk && r >= k) T[sl][4 * a_ + b_] = lr[a_];     // column k of L (diagonal: sqrt|piv|)
+                  }
+              } else if (ti == tj) {
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                  for (int b_ = 0; b_ <= a_; ++b_) T[sl][4 * a_ + b_] -= sgn * lr[a_] * lc[b_];
+              } else {
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                  for (int b_ = 0; b_ < 4; ++b_) T[sl][4 * a_ + b_] -= sgn * lr[a_] * lc[b_];
+              }
+            }
+          }
+        }
+        if (!okp) return false;
         par.sync();
-        for (int r = k + tid; r < MROWS; r += nt) sm.M[r * LDM + k] *= inv;    // M[k][k] becomes sgn * sqrt|piv|
-        par.sync();
-        const int nrem = MROWS - (k + 1), ncol = NZA - (k + 1);
-        for (int t = tid; t < nrem * ncol; t += nt) {
-          const int r = k + 1 + t / ncol, cc = k + 1 + t % ncol;
-          if (cc > r) continue;
-          sm.M[r * LDM + cc] -= sgn * sm.M[r * LDM + k] * sm.M[cc * LDM + k];
+#pragma unroll
+        for (int sl = 0; sl < Par::TPT; ++sl) {
+          if (ti_[sl] < 0) continue;
+#pragma unroll
+          for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+            for (int b_ = 0; b_ < 4; ++b_) {
+              const int r = 4 * ti_[sl] + a_, cc = 4 * tj_[sl] + b_;
+              if (r < MROWS && cc <= r && cc < NZA) sm.M[r * LDM + cc] = T[sl][4 * a_ + b_];
+            }
         }
         par.sync();
       }
-      // stream factors out; load P, p for the next stage
-      for (int t = tid; t < NA * NA; t += nt) { const int r = t / NA, cc = t % NA; if (cc <= r) fac[F_L + tri(r, cc)] = sm.M[r * LDM + cc]; }
-      for (int t = tid; t < NX * NA; t += nt) { const int r = t / NA, cc = t % NA; fac[F_LS + t] = sm.M[(XO + r) * LDM + cc]; }
-      for (int t = tid; t < NA; t += nt) fac[F_LM + t] = sm.M[GR * LDM + t];
-      for (int t = tid; t < NX * NX; t += nt) {
-        const int r = t / NX, cc = t % NX;
-        const double v = (cc <= r) ? sm.M[(XO + r) * LDM + XO + cc] : sm.M[(XO + cc) * LDM + XO + r];
-        sm.P[t] = v;
-        if (cc <= r) fac[F_P + tri(r, cc)] = v;
+      CMPC_TOC(sm, PF_CHOL);
+      // ---- gains: K = -L^-T L_S', k = -L^-T l_m (one right-hand side per thread, registers, L broadcast from
+      // shared memory); results overwrite L_S / l_m in place.  Then stream K, k, P, p out for the forward sweep.
+      for (int t = tid; t < NX + 1; t += nt) {
+        double* rowp = sm.M + (t < NX ? XO + t : GR) * LDM;
+        double v[NA];
+#pragma unroll
+        for (int q = 0; q < NA; ++q) v[q] = -rowp[q];
+#pragma unroll
+        for (int k = NA - 1; k >= 0; --k) {
+          const double zk = v[k] / sm.M[k * LDM + k];
+          v[k] = zk;
+#pragma unroll
+          for (int j = 0; j < k; ++j) v[j] -= sm.M[k * LDM + j] * zk;
+        }
+#pragma unroll
+        for (int q = 0; q < NA; ++q) sm.W[t * NA + q] = v[q];          // W (28 x 60) is free here: K staged as 29 x 34
       }
+      par.sync();
+      for (int t = tid; t < (NX + 1) * NA; t += nt) fac[F_K + t] = sm.W[t];
+      for (int r = wid; r < NX; r += nw)
+        for (int cc = lane; cc < NX; cc += nl) {
+          const double v = (cc <= r) ? sm.M[(XO + r) * LDM + XO + cc] : sm.M[(XO + cc) * LDM + XO + r];
+          sm.P[r * NX + cc] = v;
+          if (cc <= r) fac[F_P + tri(r, cc)] = v;
+        }
       for (int t = tid; t < NX; t += nt) { const double v = sm.M[GR * LDM + XO + t]; sm.pv[t] = v; fac[F_PV + t] = v; }
       par.sync();
+      CMPC_TOC(sm, PF_STORE);
     }
     return true;
   }
 
-  // ---- forward sweep: Newton step (DX, DU), new multipliers of the explicit rows (DW), full-step costates YN.
-  // With M_aa = L D L', L_S = M_xa L^-T D^-1, l_m = D^-1 L^-1 m_a:  L' z = -(l_m + L_S' dx),  z = [du ; w].
+  // ---- forward sweep: Newton step z_i = [du ; w] = k_i + K_i dx_i, dx_{i+1} = d_i + A dx_i + B du_i,
+  // full-step costates y_i = p_i + P_i dx_i.
   CMPC_HD void forward(double reg) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
     for (int t = tid; t < NX; t += nt) { sm.dxs[t] = 0.0; w.DX[t] = 0.0; }
@@ -626,36 +754,33 @@ struct Solver {
       const double* fac = w.FAC + (size_t)i * FACSZ;
       const double* rec = w.REC + (size_t)i * RECSZ;
       for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
-      for (int t = tid; t < NA * NA; t += nt) { const int r = t / NA, cc = t % NA; if (cc <= r) sm.M[r * LDM + cc] = fac[F_L + tri(r, cc)]; }
       for (int cidx = tid; cidx < NA; cidx += nt) {
-        double s = fac[F_LM + cidx];
-        for (int r = 0; r < NX; ++r) s += fac[F_LS + r * NA + cidx] * sm.dxs[r];
-        sm.zs[cidx] = -s;
+        double s = fac[F_K + NX * NA + cidx];
+#pragma unroll 4
+        for (int r = 0; r < NX; ++r) s += fac[F_K + r * NA + cidx] * sm.dxs[r];
+        sm.zs[cidx] = s;
+        if (cidx < NU) w.DU[i * NU + cidx] = s; else w.DW[i * NW + cidx - NU] = s;
       }
-      // costate of stage i (full step): y_i = p_i + P_i dx_i
-      for (int r = tid; r < NX; r += nt) {
+      // costate of stage i (full step): y_i = p_i + P_i dx_i   (threads NA.. so both loops run side by side)
+      for (int r = tid - 64; r < NX && r >= 0; r += nt) {
         double s = fac[F_PV + r];
         for (int j = 0; j < NX; ++j) s += fac[F_P + (j <= r ? tri(r, j) : tri(j, r))] * sm.dxs[j];
         w.YN[i * NX + r] = s;
       }
-      for (int t = tid; t < NX; t += nt) sm.dxn[t] = rec[Q_D + t];
+      if (nt < 64 + NX)
+        for (int r = tid; r < NX; r += nt) {
+          double s = fac[F_PV + r];
+          for (int j = 0; j < NX; ++j) s += fac[F_P + (j <= r ? tri(r, j) : tri(j, r))] * sm.dxs[j];
+          w.YN[i * NX + r] = s;
+        }
       par.sync();
-      // back substitution L' z = zs (column oriented)
-      for (int k = NA - 1; k >= 0; --k) {
-        const double zk = sm.zs[k] / sm.M[k * LDM + k];
-        par.sync();
-        if (tid == 0) sm.zs[k] = zk;
-        for (int j = tid; j < k; j += nt) sm.zs[j] -= sm.M[k * LDM + j] * zk;
-        par.sync();
-      }
-      for (int t = tid; t < NU; t += nt) w.DU[i * NU + t] = sm.zs[t];
-      for (int t = tid; t < NW; t += nt) w.DW[i * NW + t] = sm.zs[NU + t];
-      // dx_{i+1} = d + A dx + B du   (gather over the structural pattern)
+      // dx_{i+1} = d + A dx + B du   (row gather over the structural pattern)
       for (int r = tid; r < NX; r += nt) {
-        double s = sm.dxn[r];
-        for (int j = 0; j < NZ; ++j)
-          for (int q = 0; q < 4; ++q)
-            if (ba_row(j, q) == r) s += sm.bav[4 * j + q] * (j < NU ? sm.zs[j] : sm.dxs[j - NU]);
+        double s = rec[Q_D + r];
+        for (int e = sm.csr_ptr[r]; e < sm.csr_ptr[r + 1]; ++e) {
+          const int jq = sm.csr_idx[e], j = jq >> 2;
+          s += sm.bav[jq] * (j < NU ? sm.zs[j] : sm.dxs[j - NU]);
+        }
         sm.dxn[r] = s;
       }
       par.sync();
@@ -777,6 +902,16 @@ struct Solver {
   // ---- warm-started solve with a cold retry: an interior-point method started next to the boundary of a
   // changed active set can jam; a failed warm solve is repeated once from the solver's own cold start.
   CMPC_HD void run(int warm, Stats* st) {
+    if (par.tid() == 0) {
+      int n = 0;
+      for (int t = 0; t < NZ * 4; ++t) sm.barow[t] = (signed char)ba_row(t >> 2, t & 3);
+      for (int r = 0; r < NX; ++r) {
+        sm.csr_ptr[r] = (short)n;
+        for (int t = 0; t < NZ * 4; ++t) if (sm.barow[t] == r) sm.csr_idx[n++] = (unsigned char)t;
+      }
+      sm.csr_ptr[NX] = (short)n;
+    }
+    par.sync();
     run_once(warm, st);
     if (warm != 0 && st->status != ST_CONVERGED && st->status != ST_INFEASIBLE_X0) {
       const int it0 = st->iters;
@@ -832,14 +967,15 @@ struct Solver {
       }
       if (!ok) { status = ST_REGULARIZATION; break; }
       if (reg > 0.0) reg_last = reg;
-      forward(reg);
+      { CMPC_TIC(sm); forward(reg); CMPC_TOC(sm, PF_FWD); }
       double a_p, a_d, dphi;
-      slack_steps(tau, &a_p, &a_d, &dphi);
+      { CMPC_TIC(sm); slack_steps(tau, &a_p, &a_d, &dphi); CMPC_TOC(sm, PF_SLACK); }
       // short filter line search (Waechter-Biegler eq. 18-20); falls back to the full
       // fraction-to-boundary step if `ls_max` halvings are all rejected
       const double theta = ev[6], phi = ev[5] - mu * ev[7];
       if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * (theta > 1.0 ? theta : 1.0); theta_min = 1e-4 * (theta > 1.0 ? theta : 1.0); }
       double alpha = a_p; bool accepted = false; double tr[5];
+      CMPC_TIC(sm);
       for (int ls = 0; ls < c.ls_max; ++ls) {
         trial(alpha, tr);
         const double th_t = tr[0], ph_t = tr[1] - mu * tr[2];
@@ -867,8 +1003,8 @@ struct Solver {
           if (k == 30) { if (++ls_fail > 3) { status = ST_LINESEARCH; break; } }
         }
       }
-      apply_step(alpha, a_d);
-      eval(ev);
+      CMPC_TOC(sm, PF_TRIAL);
+      { CMPC_TIC(sm); apply_step(alpha, a_d); CMPC_TOC(sm, PF_APPLY); eval(ev); CMPC_TOC(sm, PF_EVAL); }
 #ifdef CMPC_TRACE
       if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",
                                it, ev[5], ev[0], ev[1], ev[2], ev[3], mu, reg, a_p, a_d, alpha, (int)accepted);

@@ -413,3 +413,33 @@ def solve(prob: Problem, w0: np.ndarray = None, opts: Options = None) -> Result:
         lam = np.clip(lam, mu / (1e10 * s), 1e10 * mu / s)
     fref = nlp.cost_reference(w)
     return Result(w, fref, nlp.violation(w), it, status, y, lam, s, E0, nfact, log)
+
+
+def unpack_problem(N, x0, com_ref, foot_ref, gamma, mass, k1, eps_reg=1e-9, w_rate=1.0) -> Problem:
+    """instance-major arrays of the C ABI (include/cmpc.h) -> Problem"""
+    com_ref = np.asarray(com_ref, float).reshape(N, 9)
+    foot_ref = np.asarray(foot_ref, float).reshape(N, 8)
+    gamma = np.asarray(gamma, float).reshape(N + 1, 2)
+    return Problem(N=N, x0=np.asarray(x0, float), com_ref=com_ref.T.copy(), pl_ref=foot_ref[:, 0:3].T.copy(),
+                   pr_ref=foot_ref[:, 3:6].T.copy(), al_ref=foot_ref[:, 6].copy(), ar_ref=foot_ref[:, 7].copy(),
+                   gl=gamma[:, 0].copy(), gr=gamma[:, 1].copy(), mass=float(mass), k1=float(k1), eps_reg=eps_reg, w_rate=w_rate)
+
+
+def neutral_start(prob: Problem) -> np.ndarray:
+    """x_i = x0, vertex f_z = m g / #contact vertices: the cold start used for all oracle-T golden vectors."""
+    N = prob.N
+    w = np.zeros(NS * N + NX)
+    for i in range(N + 1):
+        w[NS * i:NS * i + NX] = prob.x0
+    for i in range(N):
+        n = prob.gl[i] + prob.gr[i]
+        for v in range(8):
+            ge = prob.gl[i] if v < 4 else prob.gr[i]
+            w[NS * i + NX + 3 * v + 2] = ge * prob.mass * prob.grav / (4 * max(n, 1))
+    return w
+
+
+def solve_packed(N, x0, com_ref, foot_ref, gamma, mass, k1, opts: Options = None):
+    prob = unpack_problem(N, x0, com_ref, foot_ref, gamma, mass, k1)
+    r = solve(prob, neutral_start(prob), opts or Options.oracle_T())
+    return {"status": r.status, "iters": r.iters, "cost": r.cost, "viol": r.viol, "x1": r.X(N)[:, 1], "u0": r.U(N)[:, 0]}

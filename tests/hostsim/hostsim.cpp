@@ -15,6 +15,12 @@ struct ParSerial {
   int tid() const { return 0; }
   int nt() const { return 1; }
   void sync() const {}
+  int lane() const { return 0; }
+  int warp() const { return 0; }
+  int nwarps() const { return 1; }
+  int lanes() const { return 1; }
+  void sync_warp() const {}
+  static constexpr int TPT = 136;
 };
 
 extern "C" {
