@@ -180,7 +180,8 @@ def main():
     out = solver.solve_device(*prev_t, mass_t, k1_t, 0)                 # tick t-1 (cold), untimed
     torch.cuda.synchronize()
     solver.warm_save(B)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)            # the solver's launches and the timing events share this stream
+    torch.cuda.set_stream(stream)
 
     def step_device():
         solver.warm_restore(B, stream.cuda_stream)

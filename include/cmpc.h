@@ -45,7 +45,8 @@ enum {
 enum {
   CMPC_COLD = 0,          /* solver's own initial guess */
   CMPC_WARM_PRIMAL = 1,   /* states/inputs of the previous solve (what the reference does, :630-631) */
-  CMPC_WARM_FULL = 2      /* states, inputs, costates, slacks and multipliers of the previous solve */
+  CMPC_WARM_FULL = 2,     /* states, inputs, costates, slacks and multipliers of the previous solve */
+  CMPC_WARM_SHIFTED = 3   /* as FULL, moved one stage ahead first (consecutive ticks, mpc_rate * world_time_step = delta) */
 };
 
 typedef struct cmpc_config {

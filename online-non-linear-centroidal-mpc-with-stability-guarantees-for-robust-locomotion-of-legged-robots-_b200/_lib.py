@@ -17,7 +17,7 @@ _SO = os.path.join(_HERE, "libcmpc_b200.so")
 NX, NU = 20, 32
 
 STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "line_search", 3: "regularization", 4: "infeasible_x0", 5: "nan"}
-COLD, WARM_PRIMAL, WARM_FULL = 0, 1, 2
+COLD, WARM_PRIMAL, WARM_FULL, WARM_SHIFTED = 0, 1, 2, 3
 
 
 class CmpcError(RuntimeError):
@@ -187,6 +187,8 @@ class BatchSolver:
                    "iters": torch.empty(B, dtype=torch.int32, device=dev)}
         if stream is None:
             stream = torch.cuda.current_stream(x0.device).cuda_stream
+        if not stream:
+            stream = 1          # cudaStreamLegacy: torch's default stream (NULL means "the handle's own stream" in the C ABI)
         rc = self._L.cmpc_solve_device(self._h, B, x0.data_ptr(), com_ref.data_ptr(), foot_ref.data_ptr(), gamma.data_ptr(),
                                        mass.data_ptr(), k1.data_ptr(), int(warm_mode), out["x1"].data_ptr(), out["u0"].data_ptr(),
                                        out["xN"].data_ptr(), out["cost"].data_ptr(), out["viol"].data_ptr(),
@@ -212,6 +214,7 @@ class BatchSolver:
 
     def warm_restore(self, batch: int, stream=None):
         _check(self._L, self._L.cmpc_warm_restore(self._h, batch, ctypes.c_void_p(stream or 0)), "cmpc_warm_restore")
+
 
     def reset_warm(self):
         _check(self._L, self._L.cmpc_reset_warm(self._h), "cmpc_reset_warm")

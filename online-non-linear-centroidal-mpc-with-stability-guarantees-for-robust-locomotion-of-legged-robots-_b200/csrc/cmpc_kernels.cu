@@ -240,7 +240,7 @@ int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const dou
   if (!h) return fail(-1, "cmpc_solve_device: null handle");
   if (batch < 1 || batch > h->cap) return fail(-1, "cmpc_solve_device: batch exceeds the handle's capacity");
   if (!x0 || !com_ref || !foot_ref || !gamma || !mass || !k1) return fail(-1, "cmpc_solve_device: null input pointer");
-  if (warm_mode < 0 || warm_mode > 2) return fail(-1, "cmpc_solve_device: bad warm_mode");
+  if (warm_mode < 0 || warm_mode > 3) return fail(-1, "cmpc_solve_device: bad warm_mode");
   if (warm_mode != CMPC_COLD && h->warm_valid < batch) warm_mode = CMPC_COLD;     // nothing to warm-start from
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;

@@ -368,6 +368,27 @@ struct Solver {
         w.X[i * NX + IQ + v] = (i >= 1) ? w.U[(i - 1) * NU + 3 * v + 2] : 0.0;
       }
     }
+    if (warm == 3) {
+      // MPC shift: the previous tick's stage i+1 becomes this tick's stage i (the last stage is repeated).  Staged
+      // through the step buffers so the in-place move is race free.
+      for (int t = tid; t < N * NX; t += nt) { w.DX[t] = w.X[t + NX]; w.YN[t] = w.Y[t + NX]; }
+      for (int t = tid; t < (N - 1) * NU; t += nt) w.DU[t] = w.U[t + NU];
+      for (int t = tid; t < (N - 1) * NR; t += nt) {
+        const int r = t % NR;
+        // rows that exist only at stage 0 (angular momentum) keep their own history
+        w.DS[t] = (r == R_HW && t < NR) ? w.S[t] : w.S[t + NR];
+      }
+      par.sync();
+      for (int t = tid; t < N * NX; t += nt) { w.X[t] = w.DX[t]; w.Y[t] = w.YN[t]; }
+      for (int t = tid; t < (N - 1) * NU; t += nt) w.U[t] = w.DU[t];
+      for (int t = tid; t < (N - 1) * NR; t += nt) w.S[t] = w.DS[t];
+      par.sync();
+      for (int t = tid; t < (N - 1) * NR; t += nt) { const int r = t % NR; w.DS[t] = (r == R_HW && t < NR) ? w.LAM[t] : w.LAM[t + NR]; }
+      par.sync();
+      for (int t = tid; t < (N - 1) * NR; t += nt) w.LAM[t] = w.DS[t];
+      par.sync();
+      warm = 2;
+    }
     for (int t = tid; t < NX; t += nt) w.X[t] = (t < NXP) ? in.x0[t] : 0.0;      // x_0 is data
     if (warm < 2) for (int t = tid; t < (N + 1) * NX; t += nt) w.Y[t] = 0.0;
     par.sync();
@@ -913,7 +934,7 @@ struct Solver {
     }
     par.sync();
     run_once(warm, st);
-    if (warm != 0 && st->status != ST_CONVERGED && st->status != ST_INFEASIBLE_X0) {
+    if (warm != 0 && st->status != ST_CONVERGED && st->status != ST_INFEASIBLE_X0) {   // (warm 3 has shifted in place already)
       const int it0 = st->iters;
       par.sync();
       mu = 0; reg_last = 0;

@@ -31,3 +31,21 @@ def u0_err(u0, u0_star, x0, gamma0):
     d = np.where(ds[:, None], d - n * np.sum(n * d, axis=1, keepdims=True), d)
     # forces of a swing foot are pinned to ~0 by the 10|f|^2 term; they are part of the comparison as they are
     return np.linalg.norm(d, axis=1) / np.maximum(np.linalg.norm(u0s, axis=1), 1e-9)
+
+
+def golden_errors(g, k, cost, x1, u0):
+    """Errors of one result against golden instance k: the best match over the oracle's KKT points of the instance
+    (the NLP is non-convex; tests/golden/make_golden_alts.py stores the alternatives)."""
+    if "cost_alt" in g:
+        cands = [(g["cost_alt"][k, a], g["X_alt"][k, a], g["U_alt"][k, a]) for a in range(g["cost_alt"].shape[1])
+                 if np.isfinite(g["cost_alt"][k, a])]
+    else:
+        cands = [(g["cost"][k], g["X"][k], g["U"][k])]
+    best = None
+    for c, X, U in cands:
+        e = (float(cost_err(cost, c)), float(np.abs(x1[:12] - X[1, :12]).max()),
+             float(u0_err(u0, U[0], g["x0"][k], g["gamma"][k, 0])[0]))
+        score = max(e[0] / COST_TOL, e[1] / X1_TOL, e[2] / U0_TOL)
+        if best is None or score < best[0]:
+            best = (score,) + e
+    return best[1:]

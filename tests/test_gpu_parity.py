@@ -4,7 +4,7 @@ size-independent properties on full-size batches."""
 import numpy as np
 import pytest
 
-from parity import COST_TOL, U0_TOL, VIOL_TOL, X1_TOL, cost_err, u0_err
+from parity import COST_TOL, U0_TOL, VIOL_TOL, X1_TOL, cost_err, golden_errors, u0_err
 
 pytestmark = pytest.mark.gpu
 
@@ -23,11 +23,10 @@ def test_golden_parity_cold(pkg, golden, N):
     ok = g["status"] == 0
     assert ok.sum() >= len(ok) - 1
     assert (out["status"][ok] == 0).all(), out["status"]
-    assert cost_err(out["cost"], g["cost"])[ok].max() <= COST_TOL
     assert out["viol"][ok].max() <= VIOL_TOL
-    assert np.abs(out["x1"][:, :12] - g["X"][:, 1, :12])[ok].max() <= X1_TOL
-    e = u0_err(out["u0"], g["U"][:, 0], g["x0"], g["gamma"][:, 0])
-    assert e[ok].max() <= U0_TOL, e
+    for k in np.flatnonzero(ok):
+        ec, ex, eu = golden_errors(g, k, out["cost"][k], out["x1"][k], out["u0"][k])
+        assert ec <= COST_TOL and ex <= X1_TOL and eu <= U0_TOL, (int(g["ticks"][k]), ec, ex, eu)
     X, U = s.trajectory(len(ok))
     assert np.abs(X[:, 1] - out["x1"]).max() == 0.0 and np.abs(U[:, 0] - out["u0"]).max() == 0.0
 
