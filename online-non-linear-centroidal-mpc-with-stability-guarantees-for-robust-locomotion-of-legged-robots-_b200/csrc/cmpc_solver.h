@@ -53,6 +53,14 @@ static int cmpc_trace_on = 0;
 static double cmpc_dbg_rd[64];
 #endif
 
+CMPC_HD double cmpc_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 enum Status { ST_CONVERGED = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_INFEASIBLE_X0 = 4, ST_NAN = 5 };
 
 // Global-memory workspace of one instance (device resident across ticks: warm starts).
@@ -86,6 +94,7 @@ struct Smem {
   double rec[RECSZ - Q_D];   // rest of the current record (d, diag, friction, Lyapunov, ...)
   double dxs[NX], dxn[NX], zs[NA];
   double colbuf[2 * 64];     // pivot column, double buffered
+  double rdiag[NA];          // reciprocal of the stored diagonal of L
   double red[40];
   uint64_t mask[NMAX + 1];
   double acc[NMAX + 1][8];   // per-stage partial results of eval / trial passes
@@ -685,7 +694,8 @@ struct Solver {
 #endif
             // inputs need a positive pivot; an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
             if (!(sgn * piv > (k < NU ? 1e-14 : 0.0))) { okp = false; break; }    // uniform: same value for every thread
-            const double inv = 1.0 / sqrt(sgn * piv);
+            const double inv = cmpc_rsqrt(sgn * piv);
+            if (tid == 0) sm.rdiag[k] = sgn * inv;                 // reciprocal of the stored (signed) diagonal
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl) {
               const int ti = ti_[sl], tj = tj_[sl];
@@ -742,7 +752,7 @@ struct Solver {
         for (int q = 0; q < NA; ++q) v[q] = -rowp[q];
 #pragma unroll
         for (int k = NA - 1; k >= 0; --k) {
-          const double zk = v[k] / sm.M[k * LDM + k];
+          const double zk = v[k] * sm.rdiag[k];
           v[k] = zk;
 #pragma unroll
           for (int j = 0; j < k; ++j) v[j] -= sm.M[k * LDM + j] * zk;
