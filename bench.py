@@ -125,7 +125,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--horizon", type=int, default=20)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU baseline sample (0 = 4 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU baseline sample (0 = 128 per core, about 10-15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -142,7 +142,7 @@ def main():
         if rank != 0:
             return
         ncpu = os.cpu_count()
-        per_step = a.cpu_sample or 2 * ncpu
+        per_step = a.cpu_sample or 32 * ncpu
         rates = []
         for s in range(W + K):
             r, dt, conv, procs, its = cpu_reference_rate(N, per_step, seed=s)
@@ -279,7 +279,7 @@ def main():
             "gpu_launches": K * world, "roofline": roofline, "clocks": clocks}
     if world == 1 and not a.no_cpu_baseline:
         ncpu = os.cpu_count()
-        nsamp = a.cpu_sample or 4 * ncpu
+        nsamp = a.cpu_sample or 128 * ncpu
         try:
             r, dt, cconv, procs, its = cpu_reference_rate(N, nsamp, seed=0)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": procs, "kind": "port",
