@@ -648,6 +648,15 @@ struct Solver {
       }
       par.sync();
       CMPC_TOC(sm, PF_PBA);
+      // Inputs without any coupling at this stage are left out of the elimination: velocity / yaw-rate inputs of a
+      // stance foot (B column 0, cost 2 eps only) and tangential forces of a swing foot (cost 20 |f|^2 only, every
+      // other term carries gamma_e = 0).  Their column of L is sqrt(M_kk) e_k plus the gradient-row entry.
+      unsigned long long skipmask = 0ull;
+      {
+        const double gl_ = R[Q_GAM], gr_ = R[Q_GAM + 1];
+        if (gl_ > 0.5) skipmask |= (7ull << 24) | (1ull << 30); else skipmask |= 0x6DBull;            // f_x, f_y of vertices 0..3
+        if (gr_ > 0.5) skipmask |= (7ull << 27) | (1ull << 31); else skipmask |= 0x6DBull << 12;      // vertices 4..7
+      }
       // ---- partial LDL' of the [u ; w] block, right-looking, matrix held in REGISTER tiles: the 64 x 64 (padded)
       // lower triangle is cut into 4 x 4 tiles, one or two per thread; per pivot column the owners publish the
       // column through a double-buffered shared vector (one barrier per column), every thread then updates its
@@ -674,12 +683,15 @@ struct Solver {
           }
         }
         bool okp = true;
+        int nproc = 0;
         for (int tk = 0; tk < (NA + 3) / 4 && okp; ++tk) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {                          // kk static: tiles stay in registers
             const int k = 4 * tk + kk;
             if (k >= NA || !okp) break;
-            double* cb = sm.colbuf + (k & 1) * 64;
+            if ((skipmask >> k) & 1u) continue;                     // decoupled input: finished after the sweep (uniform)
+            double* cb = sm.colbuf + (nproc & 1) * 64;               // alternate per PROCESSED column (skips break k parity)
+            ++nproc;
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl)
               if (ti_[sl] >= 0 && tj_[sl] == tk) {
@@ -742,6 +754,14 @@ struct Solver {
         }
         par.sync();
       }
+      // finish the decoupled columns: L_kk = sqrt(M_kk), gradient-row entry scaled, nothing else in the column
+      for (int k = tid; k < NU; k += nt)
+        if ((skipmask >> k) & 1ull) {
+          const double piv = sm.M[k * LDM + k];
+          const double inv = cmpc_rsqrt(piv);
+          sm.M[k * LDM + k] = piv * inv; sm.rdiag[k] = inv; sm.M[GR * LDM + k] *= inv;
+        }
+      par.sync();
       CMPC_TOC(sm, PF_CHOL);
       // ---- gains: K = -L^-T L_S', k = -L^-T l_m (one right-hand side per thread, registers, L broadcast from
       // shared memory); results overwrite L_S / l_m in place.  Then stream K, k, P, p out for the forward sweep.

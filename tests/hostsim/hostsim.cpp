@@ -29,7 +29,7 @@ void hostsim_trace(int on) { cmpc::cmpc_trace_on = on; }
 
 int hostsim_work_doubles(int N) { return (int)work_doubles(N); }
 
-// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm} (NaN = keep default)
+// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min} (NaN = keep default)
 // Debug: stage-i Lagrangian gradient (60) and assembled stage block M (60x60, lower) at the iterate stored in
 // `work` (X, U, Y, S, LAM as laid out by carve_work).  Used by tests to check the analytic Hessian by finite
 // differences of the analytic gradient.
@@ -68,6 +68,10 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[6] == cfg_over[6]) c.ls_max = (int)cfg_over[6];
     if (cfg_over[7] == cfg_over[7]) c.w_rate = cfg_over[7];
     if (cfg_over[8] == cfg_over[8]) c.mu_warm = cfg_over[8];
+    if (cfg_over[9] == cfg_over[9]) c.kappa_eps = cfg_over[9];
+    if (cfg_over[10] == cfg_over[10]) c.kappa_mu = cfg_over[10];
+    if (cfg_over[11] == cfg_over[11]) c.theta_mu = cfg_over[11];
+    if (cfg_over[12] == cfg_over[12]) c.tau_min = cfg_over[12];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);

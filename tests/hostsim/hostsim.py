@@ -46,7 +46,7 @@ def solve(prob, work=None, warm=0, **over):
     L = lib()
     N = prob.N
     x0, com, foot, gam = pack(prob)
-    keys = ["eps_reg", "relax", "mu_init", "mu_final", "tol", "max_iter", "ls_max", "w_rate", "mu_warm"]
+    keys = ["eps_reg", "relax", "mu_init", "mu_final", "tol", "max_iter", "ls_max", "w_rate", "mu_warm", "kappa_eps", "kappa_mu", "theta_mu", "tau_min"]
     cfg = np.full(len(keys), np.nan)
     over.setdefault("eps_reg", prob.eps_reg)
     over.setdefault("w_rate", prob.w_rate)
