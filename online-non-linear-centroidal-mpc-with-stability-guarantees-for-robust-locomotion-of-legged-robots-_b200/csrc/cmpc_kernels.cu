@@ -55,14 +55,15 @@ __global__ void __launch_bounds__(CMPC_THREADS, CMPC_MIN_CTAS)
 cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const double* __restrict__ com_ref,
                   const double* __restrict__ foot_ref, const double* __restrict__ gamma,
                   const double* __restrict__ mass, const double* __restrict__ k1, double* work, size_t wstride,
-                  int warm, Outputs out) {
+                  int warm, Outputs out, const int32_t* __restrict__ perm, int32_t* __restrict__ last_iters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int N = c.N;
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0) for (int k = 0; k < PF_COUNT; ++k) sm.prof[k] = 0;
 #endif
-  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+  for (int slot = blockIdx.x; slot < batch; slot += gridDim.x) {
+    const int b = perm ? perm[slot] : slot;          // longest-expected-first order (see cmpc_order_kernel)
     Instance in;
     in.x0 = x0 + (size_t)NXP * b;
     in.com_ref = com_ref + (size_t)9 * N * b;
@@ -86,12 +87,27 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
       if (out.status) out.status[b] = st.status;
       if (out.iters) out.iters[b] = st.iters;
       if (out.counters) { out.counters[2 * b] = st.nfact; out.counters[2 * b + 1] = st.nreg; }
+      if (last_iters) last_iters[b] = st.nfact;
     }
     __syncthreads();
   }
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0 && out.prof) for (int k = 0; k < PF_COUNT; ++k) atomicAdd(&out.prof[k], (unsigned long long)sm.prof[k]);
 #endif
+}
+
+// Launch order for the next tick: instances sorted by the work (factorisations) their previous solve needed, longest
+// first.  CTAs are dispatched in block-index order, so the expensive instances start early and the cheap ones fill the
+// tail (LPT scheduling); iteration counts of consecutive MPC ticks are strongly correlated.  Counting sort, one CTA.
+__global__ void cmpc_order_kernel(int batch, const int32_t* __restrict__ last_iters, int32_t* __restrict__ perm) {
+  __shared__ int hist[512];
+  for (int t = threadIdx.x; t < 512; t += blockDim.x) hist[t] = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) { int k = last_iters[b]; k = k < 0 ? 0 : (k > 511 ? 511 : k); atomicAdd(&hist[511 - k], 1); }
+  __syncthreads();
+  if (threadIdx.x == 0) { int acc = 0; for (int t = 0; t < 512; ++t) { const int c = hist[t]; hist[t] = acc; acc += c; } }
+  __syncthreads();
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) { int k = last_iters[b]; k = k < 0 ? 0 : (k > 511 ? 511 : k); perm[atomicAdd(&hist[511 - k], 1)] = b; }
 }
 
 // gather / scatter between the 28-wide internal state layout and the 20-wide reference layout
@@ -138,6 +154,7 @@ struct cmpc_handle {
   double* d_in; double* d_out; int32_t* d_iout;
   double* h_in; double* h_out; int32_t* h_iout;
   int32_t* d_counters; int32_t* h_counters;
+  int32_t* d_last_iters; int32_t* d_perm;     // work of the previous solve per instance, launch order of the next one
   unsigned long long* d_prof;
   size_t in_doubles, out_doubles;
   cudaStream_t stream;
@@ -145,7 +162,7 @@ struct cmpc_handle {
   int last_batch, last_launches;
   bool have_timing;
   int warm_valid;
-  double* snap; int snap_batch; size_t iter_doubles;   // snapshot of the warm-start part of the workspace
+  double* snap; int32_t* snap_iters; int snap_batch; size_t iter_doubles;   // snapshot of the warm-start part of the workspace
 };
 
 extern "C" {
@@ -205,6 +222,9 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
   CK(cudaMalloc(&h->d_out, B * h->out_doubles * sizeof(double)), "cudaMalloc(d_out)");
   CK(cudaMalloc(&h->d_iout, B * 2 * sizeof(int32_t)), "cudaMalloc(d_iout)");
   CK(cudaMalloc(&h->d_counters, B * 2 * sizeof(int32_t)), "cudaMalloc(d_counters)");
+  CK(cudaMalloc(&h->d_last_iters, B * sizeof(int32_t)), "cudaMalloc(d_last_iters)");
+  CK(cudaMemset(h->d_last_iters, 0, B * sizeof(int32_t)), "cudaMemset(d_last_iters)");
+  CK(cudaMalloc(&h->d_perm, B * sizeof(int32_t)), "cudaMalloc(d_perm)");
   CK(cudaMallocHost(&h->h_in, B * h->in_doubles * sizeof(double)), "cudaMallocHost(h_in)");
   CK(cudaMallocHost(&h->h_out, B * h->out_doubles * sizeof(double)), "cudaMallocHost(h_out)");
   CK(cudaMallocHost(&h->h_iout, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_iout)");
@@ -224,7 +244,7 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
 int cmpc_destroy(cmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->snap); cudaFree(h->work); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_iout); cudaFree(h->d_counters);
+  cudaFree(h->snap); cudaFree(h->snap_iters); cudaFree(h->work); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_iout); cudaFree(h->d_counters); cudaFree(h->d_last_iters); cudaFree(h->d_perm);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_iout); cudaFreeHost(h->h_counters);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -247,11 +267,18 @@ int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const dou
   Outputs o{x1, u0, xN, cost, viol, status, iters, h->d_counters, h->d_prof};
   if (h->d_prof) CK(cudaMemsetAsync(h->d_prof, 0, PF_COUNT * sizeof(unsigned long long), s), "memset prof");
   CK(cudaEventRecord(h->ev0, s), "cudaEventRecord");
+  const int32_t* perm = nullptr;
+  int launches = 1;
+  if (warm_mode != CMPC_COLD) {                       // the previous solve of these instances tells how expensive they are
+    cmpc_order_kernel<<<1, 1024, 0, s>>>(batch, h->d_last_iters, h->d_perm);
+    CK(cudaGetLastError(), "cmpc_order_kernel launch");
+    perm = h->d_perm; launches = 2;
+  }
   cmpc_solve_kernel<<<batch, h->threads, sizeof(Smem), s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1,
-                                                            h->work, h->wstride, warm_mode, o);
+                                                            h->work, h->wstride, warm_mode, o, perm, h->d_last_iters);
   CK(cudaGetLastError(), "cmpc_solve_kernel launch");
   CK(cudaEventRecord(h->ev1, s), "cudaEventRecord");
-  h->last_batch = batch; h->last_launches = 1; h->have_timing = true;
+  h->last_batch = batch; h->last_launches = launches; h->have_timing = true;
   h->warm_valid = batch;
   return 0;
 }
@@ -295,7 +322,6 @@ int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const doubl
   if (viol) memcpy(viol, r, B * sizeof(double));
   if (status) memcpy(status, h->h_iout, B * sizeof(int32_t));
   if (iters) memcpy(iters, h->h_iout + B, B * sizeof(int32_t));
-  h->last_launches = 1;
   return 0;
 }
 
@@ -339,6 +365,8 @@ int cmpc_warm_save(cmpc_handle* h, int32_t batch) {
   const int N = h->cfg.N;
   h->iter_doubles = (size_t)(N + 1) * NX * 2 + (size_t)N * NU + (size_t)(N + 1) * NR * 2;   // X, U, Y, S, LAM
   if (!h->snap) CK(cudaMalloc(&h->snap, (size_t)h->cap * h->iter_doubles * sizeof(double)), "cudaMalloc(snapshot)");
+  if (!h->snap_iters) CK(cudaMalloc(&h->snap_iters, (size_t)h->cap * sizeof(int32_t)), "cudaMalloc(snapshot iters)");
+  CK(cudaMemcpyAsync(h->snap_iters, h->d_last_iters, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream), "snapshot iters");
   CK(cudaMemcpy2DAsync(h->snap, h->iter_doubles * sizeof(double), h->work, h->wstride * sizeof(double),
                        h->iter_doubles * sizeof(double), batch, cudaMemcpyDeviceToDevice, h->stream), "snapshot copy");
   CK(cudaStreamSynchronize(h->stream), "cmpc_warm_save");
@@ -352,6 +380,7 @@ int cmpc_warm_restore(cmpc_handle* h, int32_t batch, void* stream) {
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
   CK(cudaMemcpy2DAsync(h->work, h->wstride * sizeof(double), h->snap, h->iter_doubles * sizeof(double),
                        h->iter_doubles * sizeof(double), batch, cudaMemcpyDeviceToDevice, s), "snapshot restore");
+  CK(cudaMemcpyAsync(h->d_last_iters, h->snap_iters, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, s), "snapshot restore iters");
   h->warm_valid = batch;
   return 0;
 }
