@@ -343,11 +343,11 @@ CMPC_HD void stage_trial(const Config& c, const Instance& in, const Work& w, int
 template <class Par>
 struct Solver {
   const Config& c; const Instance& in; Work w; Smem& sm; Par& par;
-  double mu, reg_last;
+  double mu, reg_last, mu_scale;
   int nfact, nreg;
 
   CMPC_HD Solver(const Config& c_, const Instance& in_, const Work& w_, Smem& sm_, Par& par_)
-      : c(c_), in(in_), w(w_), sm(sm_), par(par_), mu(0), reg_last(0), nfact(0), nreg(0) {}
+      : c(c_), in(in_), w(w_), sm(sm_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0) {}
 
   CMPC_HD static int tri(int r, int cidx) { return r * (r + 1) / 2 + cidx; }
 
@@ -402,7 +402,7 @@ struct Solver {
     if (warm < 2) for (int t = tid; t < (N + 1) * NX; t += nt) w.Y[t] = 0.0;
     par.sync();
     if (warm < 2) {
-      mu = c.mu_init;
+      mu = c.mu_init * mu_scale;
       for (int i = tid; i <= N; i += nt) {
         double x[NX], u[NU], xp[NX], g[NR];
         for (int j = 0; j < NX; ++j) x[j] = w.X[i * NX + j];
@@ -950,10 +950,11 @@ struct Solver {
     par.sync();
   }
 
-  // ---- warm-started solve with a cold retry: an interior-point method started next to the boundary of a
-  // changed active set can jam; a failed warm solve is repeated once from the solver's own cold start.
+  // ---- solve with retries.  An interior-point method started next to the boundary of a changed active set can jam,
+  // and the non-convex end game occasionally stalls a few 1e-8 short of the tolerance: a failed warm solve is repeated
+  // from the solver's own cold start, a failed cold solve again with a ten times larger, then a ten times smaller initial barrier (other central paths).
   CMPC_HD void run(int warm, Stats* st) {
-    if (par.tid() == 0) {
+    if (par.tid() == 0) {                                  // structural pattern of [B A]: by column (ba_row) and by row (gather)
       int n = 0;
       for (int t = 0; t < NZ * 4; ++t) sm.barow[t] = (signed char)ba_row(t >> 2, t & 3);
       for (int r = 0; r < NX; ++r) {
@@ -963,13 +964,17 @@ struct Solver {
       sm.csr_ptr[NX] = (short)n;
     }
     par.sync();
+    // attempts: as asked (warm or cold, mu_init) -> cold, mu_init -> cold, 10 mu_init -> cold, mu_init / 10
+    mu_scale = 1.0;
     run_once(warm, st);
-    if (warm != 0 && st->status != ST_CONVERGED && st->status != ST_INFEASIBLE_X0) {   // (warm 3 has shifted in place already)
-      const int it0 = st->iters;
+    int it0 = st->iters;
+    for (int attempt = (warm == 0 ? 1 : 0); attempt < 3; ++attempt) {
+      if (st->status == ST_CONVERGED || st->status == ST_INFEASIBLE_X0) break;
+      mu_scale = (attempt == 0) ? 1.0 : (attempt == 1 ? 10.0 : 0.1);
       par.sync();
       mu = 0; reg_last = 0;
       run_once(0, st);
-      st->iters += it0;
+      st->iters += it0; it0 = st->iters;
     }
   }
 
