@@ -5,6 +5,7 @@ Layout
   csrc/            CUDA kernels + C ABI (include/cmpc.h) -> libcmpc_b200.so (built in-tree)
   _lib.py          ctypes binding of the C ABI (`BatchSolver`)
   assembly.py      per-tick parameter assembly of `solve` (MPC file :482-600), vectorised
+  fleet.py         batched closed loop on the device: table-gather assembly, solve, plant, step adjustment
   parallel.py      instance sharding over GPUs + statistics reduction (no collective on the hot path)
   centroidal_mpc_vertices.py / centroidal_mpc_vertices_payload.py
                    drop-in modules with the reference's `centroidal_mpc` class surface
@@ -14,6 +15,7 @@ There is no CPU path: creating a solver without the CUDA library or without a GP
 from ._lib import BatchSolver, CmpcError, build_library, library_path, measure_fp64_peak  # noqa: F401
 from .assembly import PlanTables, assemble_tick, pack_instances  # noqa: F401
 from .parallel import gather_stats, shard_arrays, shard_range  # noqa: F401
+from .fleet import Fleet  # noqa: F401
 
 __all__ = ["BatchSolver", "CmpcError", "build_library", "library_path", "measure_fp64_peak",
-           "PlanTables", "assemble_tick", "pack_instances", "gather_stats", "shard_arrays", "shard_range"]
+           "PlanTables", "assemble_tick", "pack_instances", "gather_stats", "shard_arrays", "shard_range", "Fleet"]
