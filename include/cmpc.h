@@ -114,8 +114,9 @@ int cmpc_reset_warm(cmpc_handle* h);
 int cmpc_last_stats(cmpc_handle* h, int64_t* iters, int64_t* nfact, int64_t* nreg, double* kernel_ms,
                     int32_t* launches);
 /* Per-phase SM cycle counters of the last solve, summed over CTAs (zeros unless built with -DCMPC_PROFILE):
- * eval, assemble, P[B A] products, factorisation, factor store, forward sweep, slack steps, trials, step. */
-int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out9);
+ * 11 values: eval, assemble, P[B A] products, factorisation, factor store, forward sweep, slack steps, trials, step,
+ * whole solves, CTA lifetimes. */
+int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out11);
 /* Bytes of device workspace per instance and shared memory per CTA. */
 int cmpc_footprint(const cmpc_handle* h, size_t* work_bytes_per_instance, size_t* smem_bytes_per_cta);
 

@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_SO = os.path.join(_HERE, "libcmpc_b200.so")
+_SO = os.environ.get("CMPC_LIB") or os.path.join(_HERE, "libcmpc_b200.so")   # CMPC_LIB: A/B builds of the same source (scripts/ab.sh)
 NX, NU = 20, 32
 
 STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "line_search", 3: "regularization", 4: "infeasible_x0", 5: "nan"}
@@ -227,9 +227,9 @@ class BatchSolver:
         return {"iters": it.value, "nfact": nf.value, "nreg": nr.value, "kernel_ms": ms.value, "launches": nl.value}
 
     def phase_cycles(self) -> dict:
-        arr = (ctypes.c_uint64 * 9)()
+        arr = (ctypes.c_uint64 * 11)()
         _check(self._L, self._L.cmpc_phase_cycles(self._h, arr), "cmpc_phase_cycles")
-        names = ["eval", "assemble", "pba", "factor", "store", "forward", "slack", "trial", "apply"]
+        names = ["eval", "assemble", "pba", "factor", "store", "forward", "slack", "trial", "apply", "solve_total", "cta_total"]
         return dict(zip(names, [int(v) for v in arr]))
 
     def footprint(self) -> dict:

@@ -5,6 +5,7 @@
 // cmpc_model.h for the NLP (both cite code/centroidal_mpc_vertices.py line by line).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -41,7 +42,8 @@ struct ParCta {
   __device__ int nwarps() const { return (int)(blockDim.x >> 5); }
   __device__ int lanes() const { return 32; }
   __device__ void sync_warp() const { __syncwarp(); }
-  static constexpr int TPT = 2;      // 4x4 register tiles per thread: 136 tiles over 128 threads
+  static constexpr int TPT = (NTILE + CMPC_THREADS - 1) / CMPC_THREADS;      // 4x4 register tiles per thread: 120 tiles over the CTA
+  static constexpr int CPT = 1;                                              // transient tiles of tile column 0 (16) per thread
 };
 
 struct Outputs {
@@ -61,6 +63,7 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
   const int N = c.N;
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0) for (int k = 0; k < PF_COUNT; ++k) sm.prof[k] = 0;
+  const long long cta_t0 = clock64();
 #endif
   for (int slot = blockIdx.x; slot < batch; slot += gridDim.x) {
     const int b = perm ? perm[slot] : slot;          // longest-expected-first order (see cmpc_order_kernel)
@@ -75,8 +78,14 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
     ParCta par;
     Solver<ParCta> sol(c, in, w, sm, par);
     Stats st;
+#ifdef CMPC_PROFILE
+    const long long solve_t0 = clock64();
+#endif
     sol.run(warm, &st);
     __syncthreads();
+#ifdef CMPC_PROFILE
+    if (threadIdx.x == 0) sm.prof[PF_SOLVE] += clock64() - solve_t0;
+#endif
     const int tid = threadIdx.x;
     if (out.x1) for (int j = tid; j < NXP; j += blockDim.x) out.x1[(size_t)NXP * b + j] = w.X[NX + j];
     if (out.xN) for (int j = tid; j < NXP; j += blockDim.x) out.xN[(size_t)NXP * b + j] = w.X[N * NX + j];
@@ -92,6 +101,7 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
     __syncthreads();
   }
 #ifdef CMPC_PROFILE
+  if (threadIdx.x == 0) sm.prof[PF_CTA] = clock64() - cta_t0;
   if (threadIdx.x == 0 && out.prof) for (int k = 0; k < PF_COUNT; ++k) atomicAdd(&out.prof[k], (unsigned long long)sm.prof[k]);
 #endif
 }
@@ -160,6 +170,7 @@ struct cmpc_handle {
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
   int last_batch, last_launches;
+  size_t smem_bytes;         // dynamic shared memory per CTA (sizeof(Smem) + the occupancy-probe padding CMPC_SMEM_PAD)
   bool have_timing;
   int warm_valid;
   double* snap; int32_t* snap_iters; int snap_batch; size_t iter_doubles;   // snapshot of the warm-start part of the workspace
@@ -174,7 +185,7 @@ int cmpc_default_config(int32_t N, cmpc_config* cfg) {
   if (!cfg || N < 1 || N > NMAX) return fail(-1, "cmpc_default_config: bad arguments (1 <= N <= 64)");
   Config c = default_config(N);
   memset(cfg, 0, sizeof(*cfg));
-  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = 128;
+  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS;
   cfg->delta = c.delta; cfg->grav = c.grav; cfg->mu_fric = c.mu_fric;
   cfg->foot_half_len = c.hl; cfg->foot_half_wid = c.hw;
   cfg->w_h = c.w_h; cfg->w_xy = c.w_xy; cfg->w_zc = c.w_zc; cfg->w_foot = c.w_foot; cfg->w_sym = c.w_sym;
@@ -235,7 +246,9 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CK(cudaEventCreate(&h->ev0), "cudaEventCreate");
   CK(cudaEventCreate(&h->ev1), "cudaEventCreate");
-  CK(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)),
+  h->smem_bytes = sizeof(Smem);
+  if (const char* pad = getenv("CMPC_SMEM_PAD")) h->smem_bytes += (size_t)atol(pad);     // profiling aid: fewer resident CTAs per SM
+  CK(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes),
      "cudaFuncSetAttribute(smem)");
   *out = h;
   return 0;
@@ -274,7 +287,7 @@ int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const dou
     CK(cudaGetLastError(), "cmpc_order_kernel launch");
     perm = h->d_perm; launches = 2;
   }
-  cmpc_solve_kernel<<<batch, h->threads, sizeof(Smem), s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1,
+  cmpc_solve_kernel<<<batch, h->threads, h->smem_bytes, s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1,
                                                             h->work, h->wstride, warm_mode, o, perm, h->d_last_iters);
   CK(cudaGetLastError(), "cmpc_solve_kernel launch");
   CK(cudaEventRecord(h->ev1, s), "cudaEventRecord");
@@ -407,12 +420,13 @@ int cmpc_last_stats(cmpc_handle* h, int64_t* iters, int64_t* nfact, int64_t* nre
   return 0;
 }
 
-/* Phase cycle counters of the last solve (all zeros unless built with -DCMPC_PROFILE): eval, assemble,
- * P[B A] products, factorisation, factor store, forward sweep, slack steps, line-search trials, step. */
-int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out9) {
-  if (!h || !out9) return fail(-1, "cmpc_phase_cycles: bad arguments");
-  for (int k = 0; k < PF_COUNT; ++k) out9[k] = 0;
-  if (h->d_prof) { CK(cudaSetDevice(h->device), "cudaSetDevice"); CK(cudaMemcpy(out9, h->d_prof, PF_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost), "D2H prof"); }
+/* Phase cycle counters of the last solve (all zeros unless built with -DCMPC_PROFILE), 11 values: eval, assemble,
+ * P[B A] products, factorisation, factor store, forward sweep, slack steps, line-search trials, step, whole solves,
+ * CTA lifetimes. */
+int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out11) {
+  if (!h || !out11) return fail(-1, "cmpc_phase_cycles: bad arguments");
+  for (int k = 0; k < PF_COUNT; ++k) out11[k] = 0;
+  if (h->d_prof) { CK(cudaSetDevice(h->device), "cudaSetDevice"); CK(cudaMemcpy(out11, h->d_prof, PF_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost), "D2H prof"); }
   return 0;
 }
 

@@ -54,6 +54,7 @@ struct Config {
   // interior-point options
   double mu_init, mu_final, tol, kappa_eps, kappa_mu, theta_mu, tau_min, bound_push;
   double mu_warm;                   // initial barrier for full warm starts
+  double warm_push, warm_comp;      // full warm start: slack floor, and cap on s*lam/mu_warm (0 = none)
   int max_iter, ls_max;
 };
 
@@ -62,11 +63,11 @@ CMPC_HD Config default_config(int N) {
   c.N = N; c.delta = 0.01; c.grav = 9.81; c.mu_fric = 0.5;
   c.hl = 0.125; c.hw = 0.065;
   c.w_h = 1000.0; c.w_xy = 1.0; c.w_zc = 2000.0; c.w_foot = 1000.0; c.w_sym = 10.0; c.w_swing = 10.0;
-  c.w_rate = 1.0; c.eps_reg = 1e-9;
+  c.w_rate = 1.0; c.eps_reg = 1e-5;
   c.pz_max = 0.76; c.box[0] = 0.01; c.box[1] = 0.005; c.box[2] = 0.00005;
   c.relax = 1e-8;
   c.mu_init = 0.1; c.mu_final = 1e-9; c.tol = 1e-8; c.kappa_eps = 10.0; c.kappa_mu = 0.2;
-  c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3;
+  c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 1e-6; c.warm_comp = 0.0;
   c.max_iter = 100; c.ls_max = 3;
   return c;
 }

@@ -24,14 +24,16 @@ constexpr int NA = NU + NW;                 // 34: augmented input block [u ; w]
 constexpr int XO = NA;                      // offset of x in the stage block [u ; w ; x]
 constexpr int NZA = NA + NX;                // 62
 constexpr int GR = NZA;                     // index of the gradient row
-constexpr int LDM = NZA + 1;                // leading dimension of the stage matrix (63, odd -> no bank conflicts)
+constexpr int MSZ = (NZA + 1) * (NZA + 2) / 2;   // stage block stored as a packed lower triangle (63 rows incl. the gradient row): 2016 doubles
+CMPC_HD constexpr int mi(int r, int c) { return r * (r + 1) / 2 + c; }   // index of M(r, c), r >= c
 constexpr int MROWS = NZA + 1;              // 62 variable rows + the gradient row
 constexpr int TRI_A = NA * (NA + 1) / 2;    // 595
 constexpr int TRI_X = NX * (NX + 1) / 2;    // 406
 // per-stage factor record streamed to global memory
 constexpr int F_K = 0, F_P = F_K + (NX + 1) * NA, F_PV = F_P + TRI_X;   // gains K (28 x 34) + k (34), cost-to-go P, p
 constexpr int FACSZ = F_PV + NX;            // 1420 doubles
-constexpr int NTILE = 16 * 17 / 2;          // 4 x 4 tiles of the padded 64 x 64 lower triangle
+constexpr int NTILE = 15 * 16 / 2;          // 4 x 4 tiles of the padded 64 x 64 lower triangle right of tile column 0 (120)
+constexpr int PSTR = 17;                    // doubles between tile rows of the pivot panel (odd: lanes with different tile rows hit different banks)
 // per-stage derivative record written by the eval pass
 constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
               Q_LG = 556, Q_LC = 568, Q_LSIG = 584, Q_HP = 585, Q_HLAM = 588, Q_HSIG = 589, Q_YH = 590,
@@ -46,12 +48,20 @@ constexpr int RECSZ = 620;
 #define CMPC_TIC(sm) do {} while (0)
 #define CMPC_TOC(sm, k) do {} while (0)
 #endif
-enum { PF_EVAL = 0, PF_ASM, PF_PBA, PF_CHOL, PF_STORE, PF_FWD, PF_SLACK, PF_TRIAL, PF_APPLY, PF_COUNT };
+enum { PF_EVAL = 0, PF_ASM, PF_PBA, PF_CHOL, PF_STORE, PF_FWD, PF_SLACK, PF_TRIAL, PF_APPLY, PF_SOLVE, PF_CTA, PF_COUNT };   // PF_SOLVE: whole solves, PF_CTA: CTA lifetime
 
 #ifdef CMPC_TRACE
 static int cmpc_trace_on = 0;
 static double cmpc_dbg_rd[64];
 #endif
+
+CMPC_HD double cmpc_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
 
 CMPC_HD double cmpc_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
@@ -85,7 +95,7 @@ CMPC_HD Work carve_work(double* base, int N) {
 
 // Shared-memory block of one instance.
 struct Smem {
-  double M[MROWS * LDM];     // stage KKT block [u;x] (+ gradient row 60), lower triangle used
+  double M[MSZ];             // stage KKT block [u ; w ; x] (+ gradient row 62), packed lower triangle
   double W[NX * NZ];         // P * [B A]
   double P[NX * NX];         // cost-to-go Hessian of stage i+1 (full symmetric)
   double pv[NX];             // cost-to-go gradient
@@ -94,6 +104,8 @@ struct Smem {
   double rec[RECSZ - Q_D];   // rest of the current record (d, diag, friction, Lyapunov, ...)
   double dxs[NX], dxn[NX], zs[NA];
   double colbuf[2 * 64];     // pivot column, double buffered
+  double panel[16 * PSTR];   // 64 x 4 panel of L (one tile column) as 16 tile rows of 16 values
+  double dpub[10];           // factored diagonal tile: reciprocal diagonal (4) and strict lower part (6)
   double rdiag[NA];          // reciprocal of the stored diagonal of L
   double red[40];
   uint64_t mask[NMAX + 1];
@@ -130,7 +142,7 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
       gl_[idx[t]] += lam[r] * val[t];
     }
     const double ar = fabs(rg);
-    prim = ar > prim ? ar : prim; theta += ar; lns += log(s[r]);
+    prim = ar > prim ? ar : prim;                                 // (theta, sum ln s come from the trial pass)
     const double sl = s[r] * lam[r];
     smax = sl > smax ? sl : smax; smin = sl < smin ? sl : smin; lsum += lam[r];
     return sig;
@@ -345,6 +357,7 @@ struct Solver {
   const Config& c; const Instance& in; Work w; Smem& sm; Par& par;
   double mu, reg_last, mu_scale;
   int nfact, nreg;
+  int tile_i[Par::TPT], tile_j[Par::TPT];     // this thread's 4 x 4 register tiles of the stage block (row, column; -1 = none)
 
   CMPC_HD Solver(const Config& c_, const Instance& in_, const Work& w_, Smem& sm_, Par& par_)
       : c(c_), in(in_), w(w_), sm(sm_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0) {}
@@ -422,8 +435,9 @@ struct Solver {
         const int i = t / NR, r = t % NR;
         if (!(sm.mask[i] & (1ull << r))) { w.S[t] = 1.0; w.LAM[t] = 0.0; continue; }
         double sv = w.S[t], lv = w.LAM[t];
-        if (!(sv > 1e-6)) sv = 1e-6;
+        if (!(sv > c.warm_push)) sv = c.warm_push;
         if (!(lv > mu / sv * 1e-3)) lv = mu / sv * 1e-3;
+        if (c.warm_comp > 0.0 && lv > mu / sv * c.warm_comp) lv = mu / sv * c.warm_comp;
         w.S[t] = sv; w.LAM[t] = lv;
       }
     }
@@ -480,19 +494,19 @@ struct Solver {
     const double* rec = w.REC + (size_t)i * RECSZ;
     for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
     for (int t = tid; t < RECSZ - Q_D; t += nt) sm.rec[t] = rec[Q_D + t];
-    for (int t = tid; t < MROWS * LDM; t += nt) sm.M[t] = 0.0;
+    for (int t = tid; t < MSZ; t += nt) sm.M[t] = 0.0;
     par.sync();
     const double* R = sm.rec - Q_D;             // R[Q_xxx] addresses the staged record
     const bool has_hw = (i == 0) && (sm.mask[0] & (1ull << R_HW));
     for (int t = tid; t < NZ; t += nt) {
-      sm.M[GR * LDM + mz(t)] = rec[Q_GC + t] + mu * rec[Q_M1 + t] + rec[Q_M2 + t];
-      sm.M[mz(t) * LDM + mz(t)] = R[Q_DIAG + t] + reg;
+      sm.M[mi(GR, mz(t))] = rec[Q_GC + t] + mu * rec[Q_M1 + t] + rec[Q_M2 + t];
+      sm.M[mi(mz(t), mz(t))] = R[Q_DIAG + t] + reg;
     }
     if (tid == 0) {
-      sm.M[NU * LDM + NU] = -1.0 / R[Q_LSIG];
-      sm.M[GR * LDM + NU] = R[Q_LRG] + mu / R[Q_LLAM];
-      sm.M[(NU + 1) * LDM + NU + 1] = has_hw ? -1.0 / R[Q_HSIG] : -1.0;
-      sm.M[GR * LDM + NU + 1] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
+      sm.M[mi(NU, NU)] = -1.0 / R[Q_LSIG];
+      sm.M[mi(GR, NU)] = R[Q_LRG] + mu / R[Q_LLAM];
+      sm.M[mi(NU + 1, NU + 1)] = has_hw ? -1.0 / R[Q_HSIG] : -1.0;
+      sm.M[mi(GR, NU + 1)] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
     }
     par.sync();
     // friction barrier blocks (lower triangle)
@@ -500,7 +514,7 @@ struct Solver {
       const int v = t / 6, e6 = t % 6;
       const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
       const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
-      sm.M[(3 * v + rr) * LDM + 3 * v + cc] += R[Q_FRIC + t];
+      sm.M[mi(3 * v + rr, 3 * v + cc)] += R[Q_FRIC + t];
     }
     par.sync();
     // symmetry-term off-diagonals (-2 w_sym / 4 between same-axis components of one foot) and rate cross terms
@@ -508,10 +522,10 @@ struct Solver {
       if (t < 36) {
         const int e = t / 18, ax = (t % 18) / 6, pr = t % 6;
         const int ka[6] = {1, 2, 2, 3, 3, 3}, kb[6] = {0, 0, 1, 0, 1, 2};
-        sm.M[(12 * e + 3 * ka[pr] + ax) * LDM + 12 * e + 3 * kb[pr] + ax] += -0.5 * c.w_sym * R[Q_GAM + e];
+        sm.M[mi(12 * e + 3 * ka[pr] + ax, 12 * e + 3 * kb[pr] + ax)] += -0.5 * c.w_sym * R[Q_GAM + e];
       } else {
         const int v = t - 36;
-        sm.M[(XO + IQ + v) * LDM + 3 * v + 2] += -2.0 * R[Q_GAMP + v / 4];
+        sm.M[mi(XO + IQ + v, 3 * v + 2)] += -2.0 * R[Q_GAMP + v / 4];
       }
     }
     par.sync();
@@ -525,7 +539,7 @@ struct Solver {
         else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
         if (lane == 0) {
           const double gv = sa * R[Q_LG + 3 * ta + xa];
-          if (ma < NU) sm.M[NU * LDM + ma] = gv; else sm.M[ma * LDM + NU] = gv;
+          if (ma < NU) sm.M[mi(NU, ma)] = gv; else sm.M[mi(ma, NU)] = gv;
         }
         if (sa == 0.0) continue;
         // same-axis partners only: bi = xa, xa + 3, ... (forces and states keep the axis in the low index)
@@ -535,7 +549,7 @@ struct Solver {
           if (bi < 24) { mb = bi; tb = 3; sb = R[Q_GAM + bi / 12]; }
           else { const int q = bi - 24; tb = q / 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xa; }
           const double v = sa * sb * R[Q_LC + 4 * ta + tb];
-          if (ma >= mb) sm.M[ma * LDM + mb] += v; else sm.M[mb * LDM + ma] += v;
+          if (ma >= mb) sm.M[mi(ma, mb)] += v; else sm.M[mi(mb, ma)] += v;
         }
       }
     }
@@ -548,7 +562,7 @@ struct Solver {
           const int a_ = t - 24 * 24;
           double ca[3] = {0, 0, 0};
           ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
-          sm.M[(NU + 1) * LDM + a_] = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
+          sm.M[mi(NU + 1, a_)] = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
           continue;
         }
         const int a_ = t / 24, b_ = t % 24;
@@ -556,7 +570,7 @@ struct Solver {
         double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
         ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
         cb[(b_ % 3 + 1) % 3] = sm.bav[4 * b_ + 1]; cb[(b_ % 3 + 2) % 3] = sm.bav[4 * b_ + 2];
-        sm.M[a_ * LDM + b_] += 2.0 * lamh * (ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2]);
+        sm.M[mi(a_, b_)] += 2.0 * lamh * (ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2]);
       }
       par.sync();
     }
@@ -570,13 +584,13 @@ struct Solver {
         if (q < 18) {
           const int a_ = (q % 9) / 3, b_ = q % 3;
           const double val = ge * Yx[a_][b_];
-          if (q < 9) sm.M[(XO + IP + b_) * LDM + 3 * v + a_] += -val;
-          else sm.M[(XO + (e ? IPR : IPL) + b_) * LDM + 3 * v + a_] += val;
+          if (q < 9) sm.M[mi(XO + IP + b_, 3 * v + a_)] += -val;
+          else sm.M[mi(XO + (e ? IPR : IPL) + b_, 3 * v + a_)] += val;
         } else {
           const int a_ = q - 18;
           const double dx_ = R[Q_DR + 2 * v], dy_ = R[Q_DR + 2 * v + 1];
           const double cr[3] = {-y2 * dy_, y2 * dx_, y0 * dy_ - y1 * dx_};   // y x (R'c), R'c = (dx_, dy_, 0)
-          sm.M[(XO + (e ? IPSR : IPSL)) * LDM + 3 * v + a_] += ge * cr[a_];
+          sm.M[mi(XO + (e ? IPSR : IPSL), 3 * v + a_)] += ge * cr[a_];
         }
       }
     }
@@ -630,7 +644,7 @@ struct Solver {
 #pragma unroll
           for (int q = 0; q < 4; ++q) { rr[q] = sm.barow[4 * a_ + q]; bv[q] = sm.bav[4 * a_ + q]; }
           if (rr[0] < 0) continue;                               // structurally empty column (previous-f_z states)
-          double* Mr = sm.M + mz(a_) * LDM;
+          double* Mr = sm.M + mi(mz(a_), 0);
           for (int b_ = lane; b_ <= a_; b_ += nl) {
             double s = 0.0;
 #pragma unroll
@@ -642,55 +656,166 @@ struct Solver {
             double s = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) { const int r2 = sm.barow[4 * b_ + q]; if (r2 >= 0) s += sm.bav[4 * b_ + q] * sm.tv[r2]; }
-            sm.M[GR * LDM + mz(b_)] += s;
+            sm.M[mi(GR, mz(b_))] += s;
           }
         }
       }
       par.sync();
       CMPC_TOC(sm, PF_PBA);
-      // Inputs without any coupling at this stage are left out of the elimination: velocity / yaw-rate inputs of a
-      // stance foot (B column 0, cost 2 eps only) and tangential forces of a swing foot (cost 20 |f|^2 only, every
-      // other term carries gamma_e = 0).  Their column of L is sqrt(M_kk) e_k plus the gradient-row entry.
-      unsigned long long skipmask = 0ull;
-      {
-        const double gl_ = R[Q_GAM], gr_ = R[Q_GAM + 1];
-        if (gl_ > 0.5) skipmask |= (7ull << 24) | (1ull << 30); else skipmask |= 0x6DBull;            // f_x, f_y of vertices 0..3
-        if (gr_ > 0.5) skipmask |= (7ull << 27) | (1ull << 31); else skipmask |= 0x6DBull << 12;      // vertices 4..7
-      }
       // ---- partial LDL' of the [u ; w] block, right-looking, matrix held in REGISTER tiles: the 64 x 64 (padded)
-      // lower triangle is cut into 4 x 4 tiles, one or two per thread; per pivot column the owners publish the
-      // column through a double-buffered shared vector (one barrier per column), every thread then updates its
-      // tile with 16 FMAs fed by 8 shared loads.  D = +1 for inputs, -1 for the explicit multipliers; the
-      // gradient row (row 62) is carried along.
+      // lower triangle is cut into 4 x 4 tiles.  The 120 tiles right of tile column 0 live one per thread for the
+      // whole factorisation; the 16 tiles of tile column 0 are final after the first block and are held only until
+      // then (by the last 16 threads).  The 32 input columns are eliminated in BLOCKS OF FOUR (one tile column):
+      //   1. the owner of the diagonal tile factors it (4 x 4, four rsqrt) and publishes L_d and the reciprocal
+      //      diagonal                                                                         -- barrier A
+      //   2. the owners of the tiles below it form their rows of L (4 x 4 forward substitution, registers) and
+      //      publish the 64 x 4 panel                                                         -- barrier B
+      //   3. every tile to the right applies the rank-4 update (64 FMAs fed by 32 shared loads).
+      // The two explicit multipliers (columns 32, 33; pivot sign -1) follow column by column.  The gradient row
+      // (row 62) is carried along.  Inputs without coupling at a stage (stance-foot velocities, swing-foot
+      // tangential forces) need no special case: their columns are zero below the diagonal.
       {
         double T[Par::TPT][16];
         int ti_[Par::TPT], tj_[Par::TPT];
 #pragma unroll
         for (int sl = 0; sl < Par::TPT; ++sl) {
-          const int tile = tid + sl * nt;
-          int ti = 0;
-          if (tile < NTILE) { while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti; }
-          ti_[sl] = tile < NTILE ? ti : -1;
-          tj_[sl] = tile < NTILE ? tile - ti * (ti + 1) / 2 : 0;
-          if (tile < NTILE) {
+          ti_[sl] = tile_i[sl]; tj_[sl] = tile_j[sl];
+          if (ti_[sl] >= 0) {
 #pragma unroll
             for (int a_ = 0; a_ < 4; ++a_)
 #pragma unroll
               for (int b_ = 0; b_ < 4; ++b_) {
-                const int r = 4 * ti + a_, cc = 4 * tj_[sl] + b_;
-                T[sl][4 * a_ + b_] = (r < MROWS && cc <= r && cc < NZA) ? sm.M[r * LDM + cc] : 0.0;
+                const int r = 4 * ti_[sl] + a_, cc = 4 * tj_[sl] + b_;
+                T[sl][4 * a_ + b_] = (r < MROWS && cc <= r && cc < NZA) ? sm.M[mi(r, cc)] : 0.0;
               }
           }
         }
         bool okp = true;
-        int nproc = 0;
-        for (int tk = 0; tk < (NA + 3) / 4 && okp; ++tk) {
+        // factor a diagonal tile held in registers; publish {1/d0..1/d3, l10, l20, l21, l30, l31, l32} and the pivot test
+        auto diag_tile = [&](double* t, int tk) {
+          const double p0 = t[0];
+          const double i0 = cmpc_rsqrt(p0);
+          const double l10 = t[4] * i0, l20 = t[8] * i0, l30 = t[12] * i0;
+          const double p1 = t[5] - l10 * l10;
+          const double i1 = cmpc_rsqrt(p1);
+          const double l21 = (t[9] - l20 * l10) * i1, l31 = (t[13] - l30 * l10) * i1;
+          const double p2 = t[10] - l20 * l20 - l21 * l21;
+          const double i2 = cmpc_rsqrt(p2);
+          const double l32 = (t[14] - l30 * l20 - l31 * l21) * i2;
+          const double p3 = t[15] - l30 * l30 - l31 * l31 - l32 * l32;
+          const double i3 = cmpc_rsqrt(p3);
+          const bool good = p0 > 1e-14 && p1 > 1e-14 && p2 > 1e-14 && p3 > 1e-14;
+#ifdef CMPC_TRACE
+          if (cmpc_trace_on && !good) printf("   pivot fail stage %d block %d piv %.3e %.3e %.3e %.3e reg %.1e\n", i, tk, p0, p1, p2, p3, reg);
+#endif
+          sm.flag = good ? 1 : 0;
+          double* d = sm.dpub;
+          d[0] = i0; d[1] = i1; d[2] = i2; d[3] = i3; d[4] = l10; d[5] = l20; d[6] = l21; d[7] = l30; d[8] = l31; d[9] = l32;
+          sm.rdiag[4 * tk] = i0; sm.rdiag[4 * tk + 1] = i1; sm.rdiag[4 * tk + 2] = i2; sm.rdiag[4 * tk + 3] = i3;
+          t[0] = p0 * i0; t[4] = l10; t[5] = p1 * i1; t[8] = l20; t[9] = l21; t[10] = p2 * i2;
+          t[12] = l30; t[13] = l31; t[14] = l32; t[15] = p3 * i3;
+        };
+        // rows of L of a tile below the diagonal tile (in place), published as tile row `ti` of the panel
+        auto panel_tile = [&](double* t, int ti) {
+          const double* d = sm.dpub;
+          const double i0 = d[0], i1 = d[1], i2 = d[2], i3 = d[3], l10 = d[4], l20 = d[5], l21 = d[6], l30 = d[7], l31 = d[8], l32 = d[9];
+          double* pl = sm.panel + PSTR * ti;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {                          // kk static: tiles stay in registers
+          for (int a_ = 0; a_ < 4; ++a_) {
+            const double v0 = t[4 * a_] * i0;
+            const double v1 = (t[4 * a_ + 1] - v0 * l10) * i1;
+            const double v2 = (t[4 * a_ + 2] - v0 * l20 - v1 * l21) * i2;
+            const double v3 = (t[4 * a_ + 3] - v0 * l30 - v1 * l31 - v2 * l32) * i3;
+            t[4 * a_] = v0; t[4 * a_ + 1] = v1; t[4 * a_ + 2] = v2; t[4 * a_ + 3] = v3;
+            pl[4 * a_] = v0; pl[4 * a_ + 1] = v1; pl[4 * a_ + 2] = v2; pl[4 * a_ + 3] = v3;
+          }
+        };
+        {   // ---- block 0: tile column 0 (transient tiles)
+          double C[Par::CPT][16];
+          int ci_[Par::CPT];
+          const int cbase = nt >= 16 ? nt - 16 : 0;
+#pragma unroll
+          for (int sl = 0; sl < Par::CPT; ++sl) {
+            const int cidx = tid - cbase + sl * nt;
+            ci_[sl] = (cidx >= 0 && cidx < 16) ? cidx : -1;
+            if (ci_[sl] >= 0) {
+#pragma unroll
+              for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ < 4; ++b_) {
+                  const int r = 4 * ci_[sl] + a_;
+                  C[sl][4 * a_ + b_] = (r < MROWS && b_ <= r) ? sm.M[mi(r, b_)] : 0.0;
+                }
+              if (ci_[sl] == 0) diag_tile(C[sl], 0);
+            }
+          }
+          par.sync();                                               // A
+          if (!sm.flag) okp = false;
+          if (okp) {
+#pragma unroll
+            for (int sl = 0; sl < Par::CPT; ++sl) {
+              if (ci_[sl] < 0) continue;
+              if (ci_[sl] > 0) panel_tile(C[sl], ci_[sl]);
+#pragma unroll
+              for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ < 4; ++b_) {
+                  const int r = 4 * ci_[sl] + a_;
+                  if (r < MROWS && b_ <= r) sm.M[mi(r, b_)] = C[sl][4 * a_ + b_];       // final: column 0..3 of L
+                }
+            }
+          }
+        }
+        for (int tk = 0; tk < NU / 4 && okp; ++tk) {
+          if (tk > 0) {
+#pragma unroll
+            for (int sl = 0; sl < Par::TPT; ++sl)
+              if (ti_[sl] == tk && tj_[sl] == tk) diag_tile(T[sl], tk);
+            par.sync();                                             // A
+            if (!sm.flag) { okp = false; break; }                   // uniform
+#pragma unroll
+            for (int sl = 0; sl < Par::TPT; ++sl)
+              if (tj_[sl] == tk && ti_[sl] > tk) panel_tile(T[sl], ti_[sl]);
+          }
+          par.sync();                                               // B
+#pragma unroll
+          for (int sl = 0; sl < Par::TPT; ++sl) {
+            const int ti = ti_[sl], tj = tj_[sl];
+            if (tj <= tk) continue;                                  // (no tile: tj = 0) tiles left of / in the block: final
+            const double* pr = sm.panel + PSTR * ti;
+            if (ti == tj) {
+              double lr[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) lr[q] = pr[q];
+#pragma unroll
+              for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ <= a_; ++b_)
+                  T[sl][4 * a_ + b_] -= lr[4 * a_] * lr[4 * b_] + lr[4 * a_ + 1] * lr[4 * b_ + 1] + lr[4 * a_ + 2] * lr[4 * b_ + 2] + lr[4 * a_ + 3] * lr[4 * b_ + 3];
+            } else {
+              const double* pc = sm.panel + PSTR * tj;
+              double lr[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) lr[q] = pr[q];
+#pragma unroll
+              for (int b_ = 0; b_ < 4; ++b_) {
+                const double v0 = pc[4 * b_], v1 = pc[4 * b_ + 1], v2 = pc[4 * b_ + 2], v3 = pc[4 * b_ + 3];
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_)
+                  T[sl][4 * a_ + b_] -= lr[4 * a_] * v0 + lr[4 * a_ + 1] * v1 + lr[4 * a_ + 2] * v2 + lr[4 * a_ + 3] * v3;
+              }
+            }
+          }
+        }
+        if (!okp) return false;
+        int nproc = 0;
+        {
+          const int tk = NU / 4;
+#pragma unroll
+          for (int kk = 0; kk < NW; ++kk) {                         // kk static: tiles stay in registers
             const int k = 4 * tk + kk;
-            if (k >= NA || !okp) break;
-            if ((skipmask >> k) & 1u) continue;                     // decoupled input: finished after the sweep (uniform)
-            double* cb = sm.colbuf + (nproc & 1) * 64;               // alternate per PROCESSED column (skips break k parity)
+            if (!okp) break;
+            double* cb = sm.colbuf + (nproc & 1) * 64;
             ++nproc;
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl)
@@ -700,12 +825,12 @@ struct Solver {
               }
             par.sync();
             const double piv = cb[k];
-            const double sgn = (k < NU) ? 1.0 : -1.0;
+            const double sgn = -1.0;
 #ifdef CMPC_TRACE
-            if (cmpc_trace_on && !(sgn * piv > (k < NU ? 1e-14 : 0.0))) printf("   pivot fail stage %d k %d piv %.3e reg %.1e\n", i, k, piv, reg);
+            if (cmpc_trace_on && !(sgn * piv > 0.0)) printf("   pivot fail stage %d k %d piv %.3e reg %.1e\n", i, k, piv, reg);
 #endif
-            // inputs need a positive pivot; an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
-            if (!(sgn * piv > (k < NU ? 1e-14 : 0.0))) { okp = false; break; }    // uniform: same value for every thread
+            // an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
+            if (!(sgn * piv > 0.0)) { okp = false; break; }    // uniform: same value for every thread
             const double inv = cmpc_rsqrt(sgn * piv);
             if (tid == 0) sm.rdiag[k] = sgn * inv;                 // reciprocal of the stored (signed) diagonal
 #pragma unroll
@@ -749,24 +874,16 @@ struct Solver {
 #pragma unroll
             for (int b_ = 0; b_ < 4; ++b_) {
               const int r = 4 * ti_[sl] + a_, cc = 4 * tj_[sl] + b_;
-              if (r < MROWS && cc <= r && cc < NZA) sm.M[r * LDM + cc] = T[sl][4 * a_ + b_];
+              if (r < MROWS && cc <= r && cc < NZA) sm.M[mi(r, cc)] = T[sl][4 * a_ + b_];
             }
         }
         par.sync();
       }
-      // finish the decoupled columns: L_kk = sqrt(M_kk), gradient-row entry scaled, nothing else in the column
-      for (int k = tid; k < NU; k += nt)
-        if ((skipmask >> k) & 1ull) {
-          const double piv = sm.M[k * LDM + k];
-          const double inv = cmpc_rsqrt(piv);
-          sm.M[k * LDM + k] = piv * inv; sm.rdiag[k] = inv; sm.M[GR * LDM + k] *= inv;
-        }
-      par.sync();
       CMPC_TOC(sm, PF_CHOL);
       // ---- gains: K = -L^-T L_S', k = -L^-T l_m (one right-hand side per thread, registers, L broadcast from
       // shared memory); results overwrite L_S / l_m in place.  Then stream K, k, P, p out for the forward sweep.
       for (int t = tid; t < NX + 1; t += nt) {
-        double* rowp = sm.M + (t < NX ? XO + t : GR) * LDM;
+        double* rowp = sm.M + mi(t < NX ? XO + t : GR, 0);
         double v[NA];
 #pragma unroll
         for (int q = 0; q < NA; ++q) v[q] = -rowp[q];
@@ -775,7 +892,7 @@ struct Solver {
           const double zk = v[k] * sm.rdiag[k];
           v[k] = zk;
 #pragma unroll
-          for (int j = 0; j < k; ++j) v[j] -= sm.M[k * LDM + j] * zk;
+          for (int j = 0; j < k; ++j) v[j] -= sm.M[mi(k, j)] * zk;
         }
 #pragma unroll
         for (int q = 0; q < NA; ++q) sm.W[t * NA + q] = v[q];          // W (28 x 60) is free here: K staged as 29 x 34
@@ -784,11 +901,11 @@ struct Solver {
       for (int t = tid; t < (NX + 1) * NA; t += nt) fac[F_K + t] = sm.W[t];
       for (int r = wid; r < NX; r += nw)
         for (int cc = lane; cc < NX; cc += nl) {
-          const double v = (cc <= r) ? sm.M[(XO + r) * LDM + XO + cc] : sm.M[(XO + cc) * LDM + XO + r];
+          const double v = (cc <= r) ? sm.M[mi(XO + r, XO + cc)] : sm.M[mi(XO + cc, XO + r)];
           sm.P[r * NX + cc] = v;
           if (cc <= r) fac[F_P + tri(r, cc)] = v;
         }
-      for (int t = tid; t < NX; t += nt) { const double v = sm.M[GR * LDM + XO + t]; sm.pv[t] = v; fac[F_PV + t] = v; }
+      for (int t = tid; t < NX; t += nt) { const double v = sm.M[mi(GR, XO + t)]; sm.pv[t] = v; fac[F_PV + t] = v; }
       par.sync();
       CMPC_TOC(sm, PF_STORE);
     }
@@ -904,7 +1021,11 @@ struct Solver {
         }
         ds[r] = dsr;
         const double dl = -lam[r] + mu / s[r] - lam[r] / s[r] * dsr;
-        if (dsr < 0.0) { const double a = -tau * s[r] / dsr; ap = a < ap ? a : ap; }
+        if (dsr < 0.0) { const double a = -tau * s[r] / dsr;
+#ifdef CMPC_TRACE
+          if (cmpc_trace_on > 1 && a < 0.3) printf("      block stage %d row %d a %.3e s %.3e ds %.3e lam %.3e\n", i, r, a, s[r], dsr, lam[r]);
+#endif
+          ap = a < ap ? a : ap; }
         if (dl < 0.0) { const double a = -tau * lam[r] / dl; ad = a < ad ? a : ad; }
         dsos += dsr / s[r];
       }
@@ -963,6 +1084,13 @@ struct Solver {
       }
       sm.csr_ptr[NX] = (short)n;
     }
+    for (int sl = 0; sl < Par::TPT; ++sl) {
+      const int tile = par.tid() + sl * par.nt();                   // tile (ti, tj), ti >= tj >= 1, row-major in the triangle
+      int ti = 0;
+      if (tile < NTILE) { while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti; }
+      tile_i[sl] = tile < NTILE ? ti + 1 : -1;
+      tile_j[sl] = tile < NTILE ? tile - ti * (ti + 1) / 2 + 1 : 0;
+    }
     par.sync();
     // attempts: as asked (warm or cold, mu_init) -> cold, mu_init -> cold, 10 mu_init -> cold, mu_init / 10
     mu_scale = 1.0;
@@ -993,10 +1121,18 @@ struct Solver {
     double theta_max = 0, theta_min = 0; bool have_theta0 = false;
     int status = ST_MAXITER, it = 0, ls_fail = 0;
     double kkt = 0.0;
+    // merit quantities of the current point (constraint violation theta, cost, sum ln s): evaluated once here, afterwards
+    // they are the values of the accepted trial point -- the eval pass needs no logarithms
+    double cur[5];
+    for (int t = par.tid(); t < (N + 1) * NX; t += par.nt()) w.DX[t] = 0.0;
+    for (int t = par.tid(); t < N * NU; t += par.nt()) w.DU[t] = 0.0;
+    for (int t = par.tid(); t < (N + 1) * NR; t += par.nt()) w.DS[t] = 0.0;
+    par.sync();
+    trial(0.0, cur);
     eval(ev);
     for (it = 0; it <= c.max_iter; ++it) {
       kkt = kkt_error(ev, c.mu_final, nrows, parts);
-      if (!(ev[0] == ev[0]) || !(ev[1] == ev[1]) || !(ev[5] == ev[5])) { status = ST_NAN; break; }
+      if (!(ev[0] == ev[0]) || !(ev[1] == ev[1]) || !(cur[1] == cur[1])) { status = ST_NAN; break; }
       if (mu <= c.mu_final && kkt <= c.tol) { status = ST_CONVERGED; break; }
       if (it == c.max_iter) break;
       // monotone barrier update (IPOPT eq. 7)
@@ -1028,7 +1164,7 @@ struct Solver {
       { CMPC_TIC(sm); slack_steps(tau, &a_p, &a_d, &dphi); CMPC_TOC(sm, PF_SLACK); }
       // short filter line search (Waechter-Biegler eq. 18-20); falls back to the full
       // fraction-to-boundary step if `ls_max` halvings are all rejected
-      const double theta = ev[6], phi = ev[5] - mu * ev[7];
+      const double theta = cur[0], phi = cur[1] - mu * cur[2];      // (theta, cost, sum ln s) of the current point
       if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * (theta > 1.0 ? theta : 1.0); theta_min = 1e-4 * (theta > 1.0 ? theta : 1.0); }
       double alpha = a_p; bool accepted = false; double tr[5];
       CMPC_TIC(sm);
@@ -1060,10 +1196,11 @@ struct Solver {
         }
       }
       CMPC_TOC(sm, PF_TRIAL);
+      for (int q = 0; q < 5; ++q) cur[q] = tr[q];
       { CMPC_TIC(sm); apply_step(alpha, a_d); CMPC_TOC(sm, PF_APPLY); eval(ev); CMPC_TOC(sm, PF_EVAL); }
 #ifdef CMPC_TRACE
       if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",
-                               it, ev[5], ev[0], ev[1], ev[2], ev[3], mu, reg, a_p, a_d, alpha, (int)accepted);
+                               it, cur[1], ev[0], ev[1], ev[2], ev[3], mu, reg, a_p, a_d, alpha, (int)accepted);
 #endif
     }
     // final report: reference cost (no eps_reg term) and max unrelaxed violation incl. dynamics defects

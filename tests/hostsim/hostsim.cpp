@@ -20,7 +20,7 @@ struct ParSerial {
   int nwarps() const { return 1; }
   int lanes() const { return 1; }
   void sync_warp() const {}
-  static constexpr int TPT = 136;
+  static constexpr int TPT = 120, CPT = 16;
 };
 
 extern "C" {
@@ -29,7 +29,7 @@ void hostsim_trace(int on) { cmpc::cmpc_trace_on = on; }
 
 int hostsim_work_doubles(int N) { return (int)work_doubles(N); }
 
-// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min} (NaN = keep default)
+// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min, warm_push, warm_comp} (NaN = keep default)
 // Debug: stage-i Lagrangian gradient (60) and assembled stage block M (60x60, lower) at the iterate stored in
 // `work` (X, U, Y, S, LAM as laid out by carve_work).  Used by tests to check the analytic Hessian by finite
 // differences of the analytic gradient.
@@ -49,7 +49,7 @@ int hostsim_stage_debug(int N, const double* x0, const double* com_ref, const do
   sol.assemble_stage(i, 0.0);
   for (int r = 0; r < 60; ++r) for (int cc = 0; cc < 60; ++cc) {
     const int a = r < NU ? r : r + NW, b = cc < NU ? cc : cc + NW;
-    M_out[r * 60 + cc] = sm->M[(a >= b ? a : b) * LDM + (a >= b ? b : a)];
+    M_out[r * 60 + cc] = sm->M[mi(a >= b ? a : b, a >= b ? b : a)];
   }
   delete sm;
   return 0;
@@ -72,6 +72,8 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[10] == cfg_over[10]) c.kappa_mu = cfg_over[10];
     if (cfg_over[11] == cfg_over[11]) c.theta_mu = cfg_over[11];
     if (cfg_over[12] == cfg_over[12]) c.tau_min = cfg_over[12];
+    if (cfg_over[13] == cfg_over[13]) c.warm_push = cfg_over[13];
+    if (cfg_over[14] == cfg_over[14]) c.warm_comp = cfg_over[14];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);

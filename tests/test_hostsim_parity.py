@@ -23,7 +23,7 @@ def problem(g, k, N):
     f = g["foot_ref"][k]
     p.pl_ref, p.pr_ref, p.al_ref, p.ar_ref = f[:, 0:3].T, f[:, 3:6].T, f[:, 6], f[:, 7]
     p.gl, p.gr = g["gamma"][k][:, 0], g["gamma"][k][:, 1]
-    p.mass, p.k1, p.eps_reg, p.w_rate = float(g["mass"]), float(g["k1"]), 1e-9, 1.0
+    p.mass, p.k1, p.eps_reg, p.w_rate = float(g["mass"]), float(g["k1"]), None, 1.0      # eps_reg: product default
     return p
 
 
