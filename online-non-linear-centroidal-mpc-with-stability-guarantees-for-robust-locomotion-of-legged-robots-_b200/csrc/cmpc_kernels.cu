@@ -42,6 +42,15 @@ struct ParCta {
   __device__ int nwarps() const { return (int)(blockDim.x >> 5); }
   __device__ int lanes() const { return 32; }
   __device__ void sync_warp() const { __syncwarp(); }
+  // asynchronous global -> shared copy of n doubles, spread over the CTA (cp.async, 8 bytes per element)
+  __device__ void copy_async(double* dst, const double* src, int n) const {
+    for (int t = (int)threadIdx.x; t < n; t += (int)blockDim.x) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + t);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + t) : "memory");
+    }
+  }
+  __device__ void commit_async() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ void wait_async() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
   static constexpr int TPT = (NTILE + CMPC_THREADS - 1) / CMPC_THREADS;      // 4x4 register tiles per thread: 120 tiles over the CTA
   static constexpr int CPT = 1;                                              // transient tiles of tile column 0 (16) per thread
 };
@@ -108,16 +117,28 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
 
 // Launch order for the next tick: instances sorted by the work (factorisations) their previous solve needed, longest
 // first.  CTAs are dispatched in block-index order, so the expensive instances start early and the cheap ones fill the
-// tail (LPT scheduling); iteration counts of consecutive MPC ticks are strongly correlated.  Counting sort, one CTA.
-__global__ void cmpc_order_kernel(int batch, const int32_t* __restrict__ last_iters, int32_t* __restrict__ perm) {
+// tail (LPT scheduling); iteration counts of consecutive MPC ticks are strongly correlated.  A contact switch that has
+// just entered the end of the horizon (schedule of the last three stages not constant) makes the previous solution a
+// poor start for the new last stages: such instances are moved forward by a fixed bonus.  Counting sort, one CTA.
+__device__ __forceinline__ int order_key(int b, int N, const int32_t* __restrict__ last_iters, const double* __restrict__ gamma) {
+  int k = last_iters[b];
+  if (gamma) {
+    const double* g = gamma + (size_t)2 * (N + 1) * b + 2 * (N - 2);          // stages N-2, N-1, N
+    if (N >= 2 && (g[0] != g[2] || g[1] != g[3] || g[2] != g[4] || g[3] != g[5])) k += 8;
+  }
+  return k < 0 ? 0 : (k > 511 ? 511 : k);
+}
+
+__global__ void cmpc_order_kernel(int batch, int N, const int32_t* __restrict__ last_iters, const double* __restrict__ gamma,
+                                  int32_t* __restrict__ perm) {
   __shared__ int hist[512];
   for (int t = threadIdx.x; t < 512; t += blockDim.x) hist[t] = 0;
   __syncthreads();
-  for (int b = threadIdx.x; b < batch; b += blockDim.x) { int k = last_iters[b]; k = k < 0 ? 0 : (k > 511 ? 511 : k); atomicAdd(&hist[511 - k], 1); }
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) atomicAdd(&hist[511 - order_key(b, N, last_iters, gamma)], 1);
   __syncthreads();
   if (threadIdx.x == 0) { int acc = 0; for (int t = 0; t < 512; ++t) { const int c = hist[t]; hist[t] = acc; acc += c; } }
   __syncthreads();
-  for (int b = threadIdx.x; b < batch; b += blockDim.x) { int k = last_iters[b]; k = k < 0 ? 0 : (k > 511 ? 511 : k); perm[atomicAdd(&hist[511 - k], 1)] = b; }
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) perm[atomicAdd(&hist[511 - order_key(b, N, last_iters, gamma)], 1)] = b;
 }
 
 // gather / scatter between the 28-wide internal state layout and the 20-wide reference layout
@@ -250,6 +271,11 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
   if (const char* pad = getenv("CMPC_SMEM_PAD")) h->smem_bytes += (size_t)atol(pad);     // profiling aid: fewer resident CTAs per SM
   CK(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes),
      "cudaFuncSetAttribute(smem)");
+#if CMPC_MIN_CTAS >= 4
+  // more than three resident CTAs per SM need a shared-memory carve-out beyond the driver's default choice
+  CK(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared),
+     "cudaFuncSetAttribute(carveout)");
+#endif
   *out = h;
   return 0;
 }
@@ -283,7 +309,7 @@ int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const dou
   const int32_t* perm = nullptr;
   int launches = 1;
   if (warm_mode != CMPC_COLD) {                       // the previous solve of these instances tells how expensive they are
-    cmpc_order_kernel<<<1, 1024, 0, s>>>(batch, h->d_last_iters, h->d_perm);
+    cmpc_order_kernel<<<1, 1024, 0, s>>>(batch, h->cfg.N, h->d_last_iters, gamma, h->d_perm);
     CK(cudaGetLastError(), "cmpc_order_kernel launch");
     perm = h->d_perm; launches = 2;
   }

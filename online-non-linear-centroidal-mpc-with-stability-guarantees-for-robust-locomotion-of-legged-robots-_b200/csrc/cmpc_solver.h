@@ -30,8 +30,10 @@ constexpr int MROWS = NZA + 1;              // 62 variable rows + the gradient r
 constexpr int TRI_A = NA * (NA + 1) / 2;    // 595
 constexpr int TRI_X = NX * (NX + 1) / 2;    // 406
 // per-stage factor record streamed to global memory
-constexpr int F_K = 0, F_P = F_K + (NX + 1) * NA, F_PV = F_P + TRI_X;   // gains K (28 x 34) + k (34), cost-to-go P, p
-constexpr int FACSZ = F_PV + NX;            // 1420 doubles
+constexpr int KSZ = (NX + 1) * NA;          // gains K (28 x 34) + k (34)
+constexpr int F_K = 0, F_P = F_K + KSZ, F_PV = F_P + NX * NX;   // K | k, cost-to-go P (full, symmetric: coalesced reads), p
+constexpr int FACSZ = F_PV + NX;            // 1798 doubles
+constexpr int FWDBUF = KSZ + NX;            // forward sweep staging of one stage: K | k | d
 constexpr int NTILE = 15 * 16 / 2;          // 4 x 4 tiles of the padded 64 x 64 lower triangle right of tile column 0 (120)
 constexpr int PSTR = 17;                    // doubles between tile rows of the pivot panel (odd: lanes with different tile rows hit different banks)
 // per-stage derivative record written by the eval pass
@@ -903,7 +905,7 @@ struct Solver {
         for (int cc = lane; cc < NX; cc += nl) {
           const double v = (cc <= r) ? sm.M[mi(XO + r, XO + cc)] : sm.M[mi(XO + cc, XO + r)];
           sm.P[r * NX + cc] = v;
-          if (cc <= r) fac[F_P + tri(r, cc)] = v;
+          fac[F_P + r * NX + cc] = v;
         }
       for (int t = tid; t < NX; t += nt) { const double v = sm.M[mi(GR, XO + t)]; sm.pv[t] = v; fac[F_PV + t] = v; }
       par.sync();
@@ -912,54 +914,73 @@ struct Solver {
     return true;
   }
 
-  // ---- forward sweep: Newton step z_i = [du ; w] = k_i + K_i dx_i, dx_{i+1} = d_i + A dx_i + B du_i,
-  // full-step costates y_i = p_i + P_i dx_i.
+  // ---- forward sweep: Newton step z_i = [du ; w] = k_i + K_i dx_i, dx_{i+1} = d_i + A dx_i + B du_i (sequential: two
+  // barriers per stage, the next stage's K | k | d | [B A] values arrive by asynchronous copy while the current stage
+  // is computed), then the full-step costates y_i = p_i + P_i dx_i of all stages at once.
+  CMPC_HD void stage_in(int i, double* kb, double* bb) {
+    const double* fac = w.FAC + (size_t)i * FACSZ;
+    const double* rec = w.REC + (size_t)i * RECSZ;
+    par.copy_async(kb, fac + F_K, KSZ);
+    par.copy_async(kb + KSZ, rec + Q_D, NX);
+    par.copy_async(bb, rec + Q_BA, NZ * 4);
+    par.commit_async();
+  }
+
   CMPC_HD void forward(double reg) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
-    for (int t = tid; t < NX; t += nt) { sm.dxs[t] = 0.0; w.DX[t] = 0.0; }
+    double* dxall = sm.M;                                        // dx of all stages, (N + 1) x NX: the stage block is idle here
+    double* kbuf[2] = {sm.W, sm.W + FWDBUF};                     // W | P storage (contiguous, idle here)
+    double* bbuf[2] = {sm.bav, sm.W + 2 * FWDBUF};
+    static_assert(2 * FWDBUF + NZ * 4 <= NX * NZ + NX * NX, "forward staging must fit in W | P");
+    static_assert((NMAX + 1) * NX <= MSZ, "dx of all stages must fit in the stage block storage");
+    for (int t = tid; t < NX; t += nt) { dxall[t] = 0.0; w.DX[t] = 0.0; }
+    stage_in(0, kbuf[0], bbuf[0]);
+    par.wait_async();
     par.sync();
     for (int i = 0; i < N; ++i) {
-      const double* fac = w.FAC + (size_t)i * FACSZ;
-      const double* rec = w.REC + (size_t)i * RECSZ;
-      for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
+      const int cur = i & 1;
+      if (i + 1 < N) stage_in(i + 1, kbuf[cur ^ 1], bbuf[cur ^ 1]);
+      const double* K = kbuf[cur];
+      const double* bav = bbuf[cur];
+      const double* dx = dxall + i * NX;
       for (int cidx = tid; cidx < NA; cidx += nt) {
-        double s = fac[F_K + NX * NA + cidx];
-#pragma unroll 4
-        for (int r = 0; r < NX; ++r) s += fac[F_K + r * NA + cidx] * sm.dxs[r];
+        double s0 = K[NX * NA + cidx], s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < NX; r += 2) { s0 += K[r * NA + cidx] * dx[r]; s1 += K[(r + 1) * NA + cidx] * dx[r + 1]; }
+        const double s = s0 + s1;
         sm.zs[cidx] = s;
         if (cidx < NU) w.DU[i * NU + cidx] = s; else w.DW[i * NW + cidx - NU] = s;
       }
-      // costate of stage i (full step): y_i = p_i + P_i dx_i   (threads NA.. so both loops run side by side)
-      for (int r = tid - 64; r < NX && r >= 0; r += nt) {
-        double s = fac[F_PV + r];
-        for (int j = 0; j < NX; ++j) s += fac[F_P + (j <= r ? tri(r, j) : tri(j, r))] * sm.dxs[j];
-        w.YN[i * NX + r] = s;
-      }
-      if (nt < 64 + NX)
-        for (int r = tid; r < NX; r += nt) {
-          double s = fac[F_PV + r];
-          for (int j = 0; j < NX; ++j) s += fac[F_P + (j <= r ? tri(r, j) : tri(j, r))] * sm.dxs[j];
-          w.YN[i * NX + r] = s;
-        }
       par.sync();
       // dx_{i+1} = d + A dx + B du   (row gather over the structural pattern)
       for (int r = tid; r < NX; r += nt) {
-        double s = rec[Q_D + r];
+        double s = K[KSZ + r];
         for (int e = sm.csr_ptr[r]; e < sm.csr_ptr[r + 1]; ++e) {
           const int jq = sm.csr_idx[e], j = jq >> 2;
-          s += sm.bav[jq] * (j < NU ? sm.zs[j] : sm.dxs[j - NU]);
+          s += bav[jq] * (j < NU ? sm.zs[j] : dx[j - NU]);
         }
-        sm.dxn[r] = s;
+        dxall[(i + 1) * NX + r] = s;
+        w.DX[(i + 1) * NX + r] = s;
       }
-      par.sync();
-      for (int t = tid; t < NX; t += nt) { sm.dxs[t] = sm.dxn[t]; w.DX[(i + 1) * NX + t] = sm.dxn[t]; }
+      par.wait_async();
       par.sync();
     }
-    {   // terminal costate: y_N = p_N + P_N dx_N  (P_N diagonal)
-      const double* rec = w.REC + (size_t)N * RECSZ;
-      for (int r = tid; r < NX; r += nt)
-        w.YN[N * NX + r] = rec[Q_GC + 32 + r] + mu * rec[Q_M1 + 32 + r] + rec[Q_M2 + 32 + r]
-                         + (rec[Q_DIAG + 32 + r] + reg) * sm.dxs[r];
+    // costates (full step) of all stages: y_i = p_i + P_i dx_i, terminal y_N = p_N + P_N dx_N (P_N diagonal)
+    for (int t = tid; t < (N + 1) * NX; t += nt) {
+      const int i = t / NX, r = t - i * NX;
+      const double* dx = dxall + i * NX;
+      double s;
+      if (i < N) {
+        const double* fac = w.FAC + (size_t)i * FACSZ;
+        double s0 = fac[F_PV + r], s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; j += 2) { s0 += fac[F_P + j * NX + r] * dx[j]; s1 += fac[F_P + (j + 1) * NX + r] * dx[j + 1]; }
+        s = s0 + s1;
+      } else {
+        const double* rec = w.REC + (size_t)N * RECSZ;
+        s = rec[Q_GC + 32 + r] + mu * rec[Q_M1 + 32 + r] + rec[Q_M2 + 32 + r] + (rec[Q_DIAG + 32 + r] + reg) * dx[r];
+      }
+      w.YN[t] = s;
     }
     par.sync();
   }

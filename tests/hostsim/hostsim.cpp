@@ -20,6 +20,9 @@ struct ParSerial {
   int nwarps() const { return 1; }
   int lanes() const { return 1; }
   void sync_warp() const {}
+  void copy_async(double* dst, const double* src, int n) const { for (int t = 0; t < n; ++t) dst[t] = src[t]; }
+  void commit_async() const {}
+  void wait_async() const {}
   static constexpr int TPT = 120, CPT = 16;
 };
 
