@@ -130,7 +130,25 @@ class ClockSampler:
                 "samples": len(mhz)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner, torchrun
+    # notices of child processes) is sent to stderr for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -172,7 +190,7 @@ def main():
                                  "sample": "%d instances per step of the same N=%d tick replay, primal warm start from tick t-1, restated "
                                            "reference (oracle/ipm_c: CasADi/IPOPT not installable offline), one process per core" % (per_step, N)},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -308,7 +326,7 @@ def main():
                                               % (nsamp, N, dt, cconv, its, oracle_name())}
         except Exception as e:  # the baseline is a reported extra: never lose the bench line over it
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
