@@ -220,6 +220,41 @@ CMPC_HD double lyapunov(const Config& c, const Instance& in, int i, const double
   return q;
 }
 
+// Curvature of the Lyapunov row in xi-space, C (x) I_3, C = T' Hz T: depends on (k1, delta, m) only -> once per instance.
+CMPC_HD void lyapunov_consts(const Config& c, const Instance& in, double* C) {
+  const double d = c.delta, m = in.mass, k1 = in.k1;
+  const double T[3][4] = {{1.0, d, 0.0, 0.0}, {k1, k1 * d + 1.0, 0.0, d / m}, {0.0, 0.0, 1.0 / m, 1.0 / m}};
+  const double Hz[3][3] = {{-2.0 * k1, 1.0 - k1 * k1, 0.0}, {1.0 - k1 * k1, 2.0 * k1, 1.0}, {0.0, 1.0, 0.0}};
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      double s = 0.0;
+      for (int p = 0; p < 3; ++p)
+        for (int r = 0; r < 3; ++r) s += T[p][a] * Hz[p][r] * T[r][b];
+      C[4 * a + b] = s;
+    }
+}
+
+// Lyapunov row value and gradient wrt xi = (p, v, theta, F) (12 values), no local arrays.
+CMPC_HD double lyapunov_grad(const Config& c, const Instance& in, int i, const double* x, const double* F, double* G) {
+  const double d = c.delta, m = in.mass, k1 = in.k1;
+  const double* ref = in.com_ref + 9 * i;
+  const double T[3][4] = {{1.0, d, 0.0, 0.0}, {k1, k1 * d + 1.0, 0.0, d / m}, {0.0, 0.0, 1.0 / m, 1.0 / m}};
+  double q = 0.0;
+  for (int j = 0; j < 3; ++j) {
+    const double grav = (j == 2) ? -c.grav : 0.0;
+    const double vp = x[IV + j] + d * (grav + F[j] / m);
+    const double z1 = x[IP + j] + d * x[IV + j] - ref[j];
+    const double z2 = k1 * z1 + vp - ref[3 + j];
+    const double ae = F[j] / m + grav - ref[6 + j] + x[ITH + j] / m;
+    q += -k1 * z1 * z1 + k1 * z2 * z2 + (1.0 - k1 * k1) * z1 * z2 + z2 * ae;
+    const double g1 = -2.0 * k1 * z1 + (1.0 - k1 * k1) * z2;
+    const double g2 = 2.0 * k1 * z2 + (1.0 - k1 * k1) * z1 + ae;
+    const double g3 = z2;
+    for (int a = 0; a < 4; ++a) G[3 * a + j] = T[0][a] * g1 + T[1][a] * g2 + T[2][a] * g3;
+  }
+  return q;
+}
+
 // All inequality rows of stage i as g <= 0 (unrelaxed).  xpred = phi_i(x,u) (needed for the hw row).
 // Rows outside `mask` are left untouched.
 CMPC_HD void stage_ineq(const Config& c, const Instance& in, int i, uint64_t mask, const double* x,

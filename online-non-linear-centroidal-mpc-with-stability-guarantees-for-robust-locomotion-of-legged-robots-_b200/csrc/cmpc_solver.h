@@ -39,8 +39,9 @@ constexpr int PSTR = 17;                    // doubles between tile rows of the 
 // per-stage derivative record written by the eval pass
 constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
               Q_LG = 556, Q_LC = 568, Q_LSIG = 584, Q_HP = 585, Q_HLAM = 588, Q_HSIG = 589, Q_YH = 590,
-              Q_GAM = 593, Q_GAMP = 595, Q_DR = 600, Q_LRG = 616, Q_LLAM = 617, Q_HRG = 618;
-constexpr int RECSZ = 620;
+              Q_GAM = 593, Q_GAMP = 595, Q_DR = 600, Q_LRG = 616, Q_LLAM = 617, Q_HRG = 618,
+              Q_RG = 620;                     // row residuals g - relax + s of the condensed rows (56 slots, by row)
+constexpr int RECSZ = Q_RG + NR;            // 676
 
 // optional phase timers (cycles, thread 0 of each CTA): -DCMPC_PROFILE
 #if defined(CMPC_PROFILE) && defined(__CUDA_ARCH__)
@@ -109,6 +110,7 @@ struct Smem {
   double panel[16 * PSTR];   // 64 x 4 panel of L (one tile column) as 16 tile rows of 16 values
   double dpub[10];           // factored diagonal tile: reciprocal diagonal (4) and strict lower part (6)
   double rdiag[NA];          // reciprocal of the stored diagonal of L
+  double lyapC[16];          // curvature of the Lyapunov row in (p, v, theta, F) space (per instance)
   double red[40];
   uint64_t mask[NMAX + 1];
   double acc[NMAX + 1][8];   // per-stage partial results of eval / trial passes
@@ -139,6 +141,7 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
   auto row = [&](int r, double gval, const int* idx, const double* val, int nnz, bool explicit_row = false) {
     const double rg = gval - c.relax + s[r];
     const double sig = lam[r] / s[r];
+    if (!explicit_row) rec[Q_RG + r] = rg;
     for (int t = 0; t < nnz; ++t) {
       if (!explicit_row) { m1[idx[t]] += val[t] / s[r]; m2[idx[t]] += sig * rg * val[t]; }
       gl_[idx[t]] += lam[r] * val[t];
@@ -353,6 +356,29 @@ CMPC_HD void stage_trial(const Config& c, const Instance& in, const Work& w, int
   acc[4] = stage_cost(c, in, i, x, u, false);
 }
 
+// Per-stage scratch of the eval pass (aliases the stage-block storage M | W | P, idle outside the backward sweep).
+struct EvalScratch {
+  double cs[2], sn[2];       // cos / sin of the two foot yaws
+  double part[8][10];        // per vertex: f (3), r x f (3), (R'c) x f (3), y_h . ((R c) x f)
+  double sum[17];            // Fe[2][3], T[3] (gamma-weighted), dT[2][3], psq[2]
+  double F[3], xph[3];       // total contact force, predicted angular momentum
+  double LG[12];             // gradient of the Lyapunov row wrt (p, v, theta, F)
+  double sc[6];              // sigma, residual, multiplier of the Lyapunov row and of the angular-momentum row
+  double st[11][5];          // per role: prim_inf, dual_inf, max s*lam, min s*lam, sum |y| + lam
+};
+constexpr int ECH = (int)((sizeof(double) * (MSZ + NX * NZ + NX * NX)) / sizeof(EvalScratch));   // stages per chunk (25)
+static_assert(ECH >= 8, "eval scratch does not fit");
+
+// Per-stage scratch of the trial pass (same storage as the eval scratch).
+struct TrialScratch {
+  double cs[2], sn[2];
+  double part[8][7];         // per vertex: f (3), r x f (3), |f|^2
+  double sum[11];            // Fe[2][3], T[3] (gamma-weighted), s2[2]
+  double st[10][5];          // per role: theta, cost (with reg), sum ln s, max violation, cost (reference)
+};
+constexpr int TCH = (int)((sizeof(double) * (MSZ + NX * NZ + NX * NX)) / sizeof(TrialScratch));   // stages per chunk (37)
+static_assert(TCH >= 8, "trial scratch does not fit");
+
 // ---------------------------------------------------------------------------------------------
 template <class Par>
 struct Solver {
@@ -446,12 +472,352 @@ struct Solver {
     par.sync();
   }
 
-  // ---- eval pass + reductions.  out: prim, dual, smax, smin, scale sums, cost, theta, lns
+  // ---- eval pass + reductions.  out: prim, dual, smax, smin, scale sums (out[5..7] unused: the merit quantities come
+  // from the trial pass).  CTA-wide: work items are (stage, role) pairs -- 8 vertex roles (friction rows, force columns),
+  // a CoM role (p, v, h, theta) and a feet role (foot poses, foot inputs) -- in short barrier-separated phases, all
+  // temporaries in registers or in the per-stage scratch: no per-thread arrays.
+#ifdef CMPC_EVAL_SERIAL
   CMPC_HD void eval(double* out) {
     const int N = c.N;
     for (int i = par.tid(); i <= N; i += par.nt()) stage_derivs(c, in, w, i, sm.mask[i], mu, sm.acc[i]);
     par.sync();
-    // tiny reduction over <= 61 stages done redundantly by every thread (broadcast reads)
+    reduce_acc(out);
+  }
+#else
+  CMPC_HD static void stat_row(double* st, double rg, double s, double lam) {
+    const double ar = fabs(rg), sl = s * lam;
+    st[0] = ar > st[0] ? ar : st[0]; st[2] = sl > st[2] ? sl : st[2]; st[3] = sl < st[3] ? sl : st[3]; st[4] += lam;
+  }
+  CMPC_HD static void stat_dual(double* st, double r) { const double ar = fabs(r); st[1] = ar > st[1] ? ar : st[1]; }
+
+  CMPC_HD void eval(double* out) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    EvalScratch* es = reinterpret_cast<EvalScratch*>(sm.M);
+    const double d = c.delta, m = in.mass, k1 = in.k1;
+    for (int i0 = 0; i0 <= N; i0 += ECH) {
+      const int ns = (N + 1 - i0) < ECH ? (N + 1 - i0) : ECH;
+      // ---- P0: yaw sines / cosines; role statistics cleared
+      for (int t = tid; t < ns * 2; t += nt) {
+        const int il = t >> 1, e = t & 1, i = i0 + il;
+        const double psi = w.X[i * NX + (e ? IPSR : IPSL)];
+        es[il].cs[e] = cos(psi); es[il].sn[e] = sin(psi);
+      }
+      for (int t = tid; t < ns * 11; t += nt) {
+        double* st = es[t / 11].st[t % 11];
+        st[0] = 0.0; st[1] = 0.0; st[2] = 0.0; st[3] = 1e300; st[4] = 0.0;
+      }
+      par.sync();
+      // ---- P1: per-vertex partial sums
+      for (int t = tid; t < ns * 8; t += nt) {
+        const int il = t >> 3, v = t & 7, i = i0 + il;
+        if (i >= N) continue;
+        const int e = v >> 2, k = v & 3;
+        const double* x = w.X + i * NX; const double* u = w.U + i * NU; const double* yn = w.Y + (i + 1) * NX;
+        const double* pe = x + (e ? IPR : IPL);
+        const double cs = es[il].cs[e], sn = es[il].sn[e];
+        double cx, cy; corner(c, k, cx, cy);
+        const double rx = cs * cx - sn * cy, ry = sn * cx + cs * cy;
+        const double r0 = rx + pe[0] - x[0], r1 = ry + pe[1] - x[1], r2 = pe[2] - x[2];
+        const double dr0 = -sn * cx - cs * cy, dr1 = cs * cx - sn * cy;
+        const double f0 = u[3 * v], f1 = u[3 * v + 1], f2 = u[3 * v + 2];
+        double* p = es[il].part[v];
+        p[0] = f0; p[1] = f1; p[2] = f2;
+        p[3] = r1 * f2 - r2 * f1; p[4] = r2 * f0 - r0 * f2; p[5] = r0 * f1 - r1 * f0;
+        p[6] = dr1 * f2; p[7] = -dr0 * f2; p[8] = dr0 * f1 - dr1 * f0;
+        p[9] = yn[IH] * (ry * f2) + yn[IH + 1] * (-rx * f2) + yn[IH + 2] * (rx * f1 - ry * f0);
+      }
+      par.sync();
+      // ---- P2: sums over the vertices
+      for (int t = tid; t < ns * 17; t += nt) {
+        const int il = t / 17, q = t - il * 17, i = i0 + il;
+        if (i >= N) continue;
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double (*pt)[10] = es[il].part;
+        double s = 0.0;
+        if (q < 6) { const int e = q / 3, j = q - 3 * e; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][j]; }
+        else if (q < 9) { const int j = q - 6; for (int v = 0; v < 8; ++v) s += (v < 4 ? gl : gr) * pt[v][3 + j]; }
+        else if (q < 15) { const int e = (q - 9) / 3, j = (q - 9) - 3 * e; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][6 + j]; }
+        else { const int e = q - 15; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][9]; }
+        es[il].sum[q] = s;
+      }
+      par.sync();
+      // ---- P3: stage scalars: total force, predicted angular momentum, the two explicit rows
+      for (int il = tid; il < ns; il += nt) {
+        const int i = i0 + il;
+        if (i >= N) continue;
+        EvalScratch& E = es[il];
+        const double* x = w.X + i * NX; const double* yn = w.Y + (i + 1) * NX;
+        const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR;
+        double* rec = w.REC + (size_t)i * RECSZ;
+        const uint64_t mask = sm.mask[i];
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        for (int j = 0; j < 3; ++j) { E.F[j] = gl * E.sum[j] + gr * E.sum[3 + j]; E.xph[j] = x[IH + j] + d * E.sum[6 + j]; }
+        const double q = lyapunov_grad(c, in, i, x, E.F, E.LG);
+        double* st = E.st[10];
+        {
+          const double sv = s[R_LYAP], lv = lam[R_LYAP], rg = q - c.relax + sv;
+          stat_row(st, rg, sv, lv);
+          E.sc[0] = lv / sv; E.sc[1] = rg; E.sc[2] = lv;
+          rec[Q_LSIG] = lv / sv; rec[Q_LRG] = rg; rec[Q_LLAM] = lv;
+          for (int t = 0; t < 16; ++t) rec[Q_LC + t] = lv * sm.lyapC[t];
+          for (int t = 0; t < 12; ++t) rec[Q_LG + t] = E.LG[t];
+        }
+        E.sc[3] = 0.0; E.sc[4] = 0.0; E.sc[5] = 0.0;
+        if (mask & (1ull << R_HW)) {
+          const double ghw = E.xph[0] * E.xph[0] + E.xph[1] * E.xph[1] + E.xph[2] * E.xph[2]
+                           - (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]);
+          const double sv = s[R_HW], lv = lam[R_HW], rg = ghw - c.relax + sv;
+          stat_row(st, rg, sv, lv);
+          E.sc[3] = lv / sv; E.sc[4] = rg; E.sc[5] = lv;
+          rec[Q_HRG] = rg;
+        }
+        rec[Q_HSIG] = E.sc[3]; rec[Q_HLAM] = E.sc[5];
+        for (int j = 0; j < 3; ++j) { rec[Q_HP + j] = E.xph[j]; rec[Q_YH + j] = d * yn[IH + j]; }
+        for (int e = 0; e < 2; ++e) {
+          rec[Q_GAM + e] = e ? gr : gl;
+          rec[Q_GAMP + e] = (i >= 1) ? in.gamma[2 * (i - 1) + e] * c.w_rate : 0.0;
+        }
+      }
+      par.sync();
+      // ---- P4: the roles (role-major item order: warps stay on one code path)
+      for (int t = tid; t < ns * 10; t += nt) {
+        const int role = t / ns, il = t - role * ns, i = i0 + il;
+        const bool has_u = i < N;
+        EvalScratch& E = es[il];
+        const double* x = w.X + i * NX; const double* yi = w.Y + i * NX;
+        const double* u = w.U + (has_u ? i : 0) * NU;                 // (not read at the terminal stage)
+        const double* yn = w.Y + (has_u ? i + 1 : i) * NX;
+        const double* xn = w.X + (has_u ? i + 1 : i) * NX;
+        const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR;
+        double* rec = w.REC + (size_t)i * RECSZ;
+        const uint64_t mask = sm.mask[i];
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        double* st = E.st[role];
+        const double lamL = has_u ? E.sc[2] : 0.0, lamH = has_u ? E.sc[5] : 0.0;
+        const bool x_free = i >= 1;                                   // x_0 is data: its dual residual is not a residual
+        if (role < 8) {
+          // ---------------- vertex v: three force inputs and the previous-f_z state q_v
+          const int v = role, e = v >> 2, k = v & 3;
+          const int qi = 32 + IQ + v;
+          if (!has_u) {
+            rec[Q_GC + qi] = 0.0; rec[Q_DIAG + qi] = 0.0; rec[Q_M1 + qi] = 0.0; rec[Q_M2 + qi] = 0.0;
+            stat_dual(st, -yi[IQ + v]); st[4] += fabs(yi[IQ + v]);
+            continue;
+          }
+          const double ge = e ? gr : gl;
+          const double* pe = x + (e ? IPR : IPL);
+          const double cs = E.cs[e], sn = E.sn[e];
+          double cx, cy; corner(c, k, cx, cy);
+          const double rx = cs * cx - sn * cy, ry = sn * cx + cs * cy;
+          const double rr[3] = {rx + pe[0] - x[0], ry + pe[1] - x[1], pe[2] - x[2]};
+          rec[Q_DR + 2 * v] = -sn * cx - cs * cy; rec[Q_DR + 2 * v + 1] = cs * cx - sn * cy;
+          const double fv[3] = {u[3 * v], u[3 * v + 1], u[3 * v + 2]};
+          const double gp = (i >= 1) ? in.gamma[2 * (i - 1) + e] * c.w_rate : 0.0;
+          const double dz = fv[2] - x[IQ + v];
+          double a_gc[3], a_dg[3], a_m1[3] = {0, 0, 0}, a_m2[3] = {0, 0, 0}, a_gl[3] = {0, 0, 0};
+          for (int j = 0; j < 3; ++j) {
+            const double mean = 0.25 * E.sum[3 * e + j];
+            a_gc[j] = ge * 2.0 * c.w_sym * (fv[j] - mean) + (1.0 - ge) * 2.0 * c.w_swing * fv[j];
+            a_dg[j] = ge * 2.0 * c.w_sym * 0.75 + (1.0 - ge) * 2.0 * c.w_swing;
+          }
+          a_gc[2] += 2.0 * gp * dz; a_dg[2] += 2.0 * gp;
+          double blk[6] = {0, 0, 0, 0, 0, 0};
+          if (mask & (1ull << (R_UNI + v))) {
+            const double mf = c.mu_fric;
+            const double gv[5] = {fv[0] - mf * fv[2], -fv[0] - mf * fv[2], fv[1] - mf * fv[2], -fv[1] - mf * fv[2], -fv[2]};
+            double sg[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              const int r = (q < 4) ? R_FRIC + 4 * v + q : R_UNI + v;
+              const double sv = s[r], lv = lam[r], inv = cmpc_rcp(sv), rg = gv[q] - c.relax + sv, sig = lv * inv;
+              sg[q] = sig;
+              stat_row(st, rg, sv, lv); rec[Q_RG + r] = rg;
+              const int ax = (q < 2) ? 0 : (q < 4 ? 1 : 2);
+              const double ja = (q == 4) ? -1.0 : ((q & 1) ? -1.0 : 1.0);
+              a_m1[ax] += ja * inv; a_m2[ax] += ja * sig * rg; a_gl[ax] += ja * lv;
+              if (q < 4) { a_m1[2] += -mf * inv; a_m2[2] += -mf * sig * rg; a_gl[2] += -mf * lv; }
+            }
+            blk[0] = sg[0] + sg[1]; blk[2] = -mf * (sg[0] - sg[1]);
+            blk[3] = sg[2] + sg[3]; blk[4] = -mf * (sg[2] - sg[3]);
+            blk[5] = mf * mf * (sg[0] + sg[1] + sg[2] + sg[3]) + sg[4];
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) rec[Q_FRIC + 6 * v + q] = blk[q];
+          const bool hw = (mask >> R_HW) & 1ull;
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax) {
+            const int ui = 3 * v + ax;
+            const double c0 = d * ge / m, c1 = d * ge * rr[(ax + 2) % 3], c2 = -d * ge * rr[(ax + 1) % 3], c3 = (ax == 2) ? 1.0 : 0.0;
+            double* col = rec + Q_BA + 4 * ui;
+            col[0] = c0; col[1] = c1; col[2] = c2; col[3] = c3;
+            double glv = a_gl[ax] + lamL * ge * E.LG[9 + ax];
+            if (hw) glv += lamH * 2.0 * (E.xph[(ax + 1) % 3] * c1 + E.xph[(ax + 2) % 3] * c2);
+            double r = a_gc[ax] + glv + c0 * yn[IV + ax] + c1 * yn[IH + (ax + 1) % 3] + c2 * yn[IH + (ax + 2) % 3];
+            if (ax == 2) r += yn[IQ + v];
+            stat_dual(st, r);
+#ifdef CMPC_TRACE
+            cmpc_dbg_rd[ui] = r;
+#endif
+            rec[Q_GC + ui] = a_gc[ax]; rec[Q_DIAG + ui] = a_dg[ax]; rec[Q_M1 + ui] = a_m1[ax]; rec[Q_M2 + ui] = a_m2[ax];
+          }
+          {
+            double* col = rec + Q_BA + 4 * qi;
+            col[0] = 0.0; col[1] = 0.0; col[2] = 0.0; col[3] = 0.0;
+            const double gq = -2.0 * gp * dz;
+            rec[Q_GC + qi] = gq; rec[Q_DIAG + qi] = 2.0 * gp; rec[Q_M1 + qi] = 0.0; rec[Q_M2 + qi] = 0.0;
+            const double r = x_free ? gq - yi[IQ + v] : 0.0;
+            stat_dual(st, r);
+#ifdef CMPC_TRACE
+            cmpc_dbg_rd[qi] = r;
+#endif
+            st[4] += fabs(yi[IQ + v]);
+            // dynamics defect of q_v+ = f_z
+            const double dj = fv[2] - xn[IQ + v];
+            rec[Q_D + IQ + v] = dj;
+            const double ad = fabs(dj); st[0] = ad > st[0] ? ad : st[0];
+          }
+        } else if (role == 8) {
+          // ---------------- CoM role: p, v, h, theta
+          const double* refp = in.com_ref + 9 * (i >= 1 ? i - 1 : 0);         // tracking reference column i-1
+          const double* ref = in.com_ref + 9 * (has_u ? i : 0);               // dynamics / Lyapunov reference column i
+          const double wz = (i >= 1) ? wz_of(c, i - 1) : 0.0;
+#pragma unroll
+          for (int cidx = 0; cidx < 12; ++cidx) {
+            const int j = 32 + cidx, ax = cidx % 3;
+            double gcv = 0.0, dgv = 0.0, m1v = 0.0, m2v = 0.0, glv = 0.0;
+            double c0 = 1.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, by = 0.0;
+            if (cidx < 3) {
+              if (i >= 1) { const double wq = (cidx == 2) ? wz : c.w_xy; gcv = 2.0 * wq * (x[cidx] - refp[cidx]); dgv = 2.0 * wq; }
+              if (cidx == 2 && (mask & (1ull << R_PZ))) {
+                const double sv = s[R_PZ], lv = lam[R_PZ], inv = cmpc_rcp(sv), rg = x[IP + 2] - c.pz_max - c.relax + sv, sig = lv * inv;
+                stat_row(st, rg, sv, lv); rec[Q_RG + R_PZ] = rg;
+                m1v = inv; m2v = sig * rg; glv = lv; dgv += sig;
+              }
+              if (has_u) {
+                glv += lamL * E.LG[cidx];
+                c1 = d * k1 / m; c2 = d * E.F[(ax + 2) % 3]; c3 = -d * E.F[(ax + 1) % 3];
+                by = c0 * yn[IP + ax] + c1 * yn[ITH + ax] + c2 * yn[IH + (ax + 1) % 3] + c3 * yn[IH + (ax + 2) % 3];
+              }
+            } else if (cidx < 6) {
+              if (has_u) {
+                glv = lamL * E.LG[cidx];
+                c0 = d; c1 = 1.0; c2 = d / m;
+                by = c0 * yn[IP + ax] + c1 * yn[IV + ax] + c2 * yn[ITH + ax];
+              }
+            } else if (cidx < 9) {
+              if (has_u) { gcv = 2.0 * c.w_h * x[cidx]; dgv = 2.0 * c.w_h; by = yn[cidx]; }
+            } else {
+              if (has_u) { glv = lamL * E.LG[cidx - 3]; by = yn[cidx]; }
+            }
+            if (has_u) { double* col = rec + Q_BA + 4 * j; col[0] = c0; col[1] = c1; col[2] = c2; col[3] = c3; }
+            const double r = x_free ? gcv + glv + by - yi[cidx] : 0.0;
+            stat_dual(st, r);
+#ifdef CMPC_TRACE
+            cmpc_dbg_rd[j] = r;
+#endif
+            st[4] += fabs(yi[cidx]);
+            rec[Q_GC + j] = gcv; rec[Q_DIAG + j] = dgv; rec[Q_M1 + j] = m1v; rec[Q_M2 + j] = m2v;
+            if (has_u) {
+              double xp;
+              if (cidx < 3) xp = x[cidx] + d * x[IV + cidx];
+              else if (cidx < 6) xp = x[cidx] + d * ((cidx == 5 ? -c.grav : 0.0) + E.F[ax] / m);
+              else if (cidx < 9) xp = E.xph[ax];
+              else xp = x[cidx] + (d / m) * (k1 * (x[ax] - ref[ax]) + x[IV + ax] - ref[3 + ax]);
+              const double dj = xp - xn[cidx];
+              rec[Q_D + cidx] = dj;
+              const double ad = fabs(dj); st[0] = ad > st[0] ? ad : st[0];
+            }
+          }
+        } else {
+          // ---------------- feet role: yaw / position states of both feet, foot velocity / yaw-rate inputs
+          const double* fr = in.foot_ref + 8 * (i >= 1 ? i - 1 : 0);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double ge = e ? gr : gl;
+            const int po = e ? IPSR : IPSL, xo = e ? IPR : IPL;
+            const bool box = (i >= 1) && ((mask >> (R_BOX + 6 * e)) & 1ull);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {                                   // jj = 0: yaw, 1..3: position
+              const int cidx = (jj == 0) ? po : xo + jj - 1, j = 32 + cidx, ax = jj - 1;
+              double gcv = 0.0, dgv = 0.0, m1v = 0.0, m2v = 0.0, glv = 0.0;
+              double c1 = 0.0, c2 = 0.0, c3 = 0.0, by = 0.0;
+              if (jj == 0) {
+                if (i >= 1) { gcv = 2.0 * c.w_foot * ge * (x[po] - fr[6 + e]); dgv = 2.0 * c.w_foot * ge; }
+                if (has_u) {
+                  dgv += -d * ge * E.sum[15 + e];
+                  c1 = d * ge * E.sum[9 + 3 * e]; c2 = d * ge * E.sum[10 + 3 * e]; c3 = d * ge * E.sum[11 + 3 * e];
+                  by = yn[cidx] + c1 * yn[IH] + c2 * yn[IH + 1] + c3 * yn[IH + 2];
+                }
+              } else {
+                if (i >= 1) {
+                  const double err = x[cidx] - fr[3 * e + ax];
+                  gcv = 2.0 * c.w_foot * ge * err; dgv = 2.0 * c.w_foot * ge;
+                  if (box) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                      const int r = R_BOX + 6 * e + 2 * ax + q;
+                      const double ja = q ? -1.0 : 1.0, gval = ja * err - c.box[ax];
+                      const double sv = s[r], lv = lam[r], inv = cmpc_rcp(sv), rg = gval - c.relax + sv, sig = lv * inv;
+                      stat_row(st, rg, sv, lv); rec[Q_RG + r] = rg;
+                      m1v += ja * inv; m2v += ja * sig * rg; glv += ja * lv; dgv += sig;
+                    }
+                  }
+                }
+                if (has_u) {
+                  c1 = -d * ge * E.sum[3 * e + (ax + 2) % 3]; c2 = d * ge * E.sum[3 * e + (ax + 1) % 3];
+                  by = yn[cidx] + c1 * yn[IH + (ax + 1) % 3] + c2 * yn[IH + (ax + 2) % 3];
+                }
+              }
+              if (has_u) { double* col = rec + Q_BA + 4 * j; col[0] = 1.0; col[1] = c1; col[2] = c2; col[3] = c3; }
+              const double r = x_free ? gcv + glv + by - yi[cidx] : 0.0;
+              stat_dual(st, r);
+#ifdef CMPC_TRACE
+              cmpc_dbg_rd[j] = r;
+#endif
+              st[4] += fabs(yi[cidx]);
+              rec[Q_GC + j] = gcv; rec[Q_DIAG + j] = dgv; rec[Q_M1 + j] = m1v; rec[Q_M2 + j] = m2v;
+              if (has_u) {
+                // input driving this state: yaw rate u[30 + e], foot velocity u[24 + 3 e + ax]
+                const int ui = (jj == 0) ? 30 + e : 24 + 3 * e + ax;
+                const double bu = d * (1.0 - ge), uv = u[ui];
+                const double dj = x[cidx] + bu * uv - xn[cidx];
+                rec[Q_D + cidx] = dj;
+                const double ad = fabs(dj); st[0] = ad > st[0] ? ad : st[0];
+                double* col = rec + Q_BA + 4 * ui;
+                col[0] = bu; col[1] = 0.0; col[2] = 0.0; col[3] = 0.0;
+                const double gu = 2.0 * c.eps_reg * uv;
+                rec[Q_GC + ui] = gu; rec[Q_DIAG + ui] = 2.0 * c.eps_reg; rec[Q_M1 + ui] = 0.0; rec[Q_M2 + ui] = 0.0;
+                const double ru = gu + bu * yn[cidx];
+                stat_dual(st, ru);
+#ifdef CMPC_TRACE
+                cmpc_dbg_rd[ui] = ru;
+#endif
+              }
+            }
+          }
+        }
+      }
+      par.sync();
+      // ---- P5: roles -> stage
+      for (int il = tid; il < ns; il += nt) {
+        double prim = 0, dual = 0, smax = 0, smin = 1e300, msum = 0;
+        for (int r = 0; r < 11; ++r) {
+          const double* q = es[il].st[r];
+          prim = q[0] > prim ? q[0] : prim; dual = q[1] > dual ? q[1] : dual; smax = q[2] > smax ? q[2] : smax; smin = q[3] < smin ? q[3] : smin;
+          msum += q[4];
+        }
+        double* a = sm.acc[i0 + il];
+        a[0] = prim; a[1] = dual; a[2] = smax; a[3] = smin; a[4] = msum; a[5] = 0.0; a[6] = 0.0; a[7] = 0.0;
+      }
+      par.sync();
+    }
+    reduce_acc(out);
+  }
+#endif
+
+  // tiny reduction over <= 65 stages done redundantly by every thread (broadcast reads)
+  CMPC_HD void reduce_acc(double* out) {
+    const int N = c.N;
     double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0, cost = 0, theta = 0, lns = 0;
     for (int i = 0; i <= N; ++i) {
       const double* a = sm.acc[i];
@@ -985,70 +1351,80 @@ struct Solver {
     par.sync();
   }
 
-  // ---- slack steps ds = -(g - relax + s) - J dz, evaluated row by row; also the max step lengths.
-  // (thread-per-stage; uses the linearisation stored in the record through finite structure:
-  //  J dz is recomputed analytically row by row.)
+  // ---- slack steps ds = -(g - relax + s) - J dz row by row (the row residuals come from the eval pass), multiplier
+  // steps, the fraction-to-boundary step lengths and the directional derivative of the barrier function.
+  // CTA-wide: items are (stage, role) with the roles of the eval pass (8 vertices, CoM rows, foot rows).
   CMPC_HD void slack_steps(double tau, double* a_p, double* a_d, double* dphi) {
-    const int N = c.N;
-    for (int i = par.tid(); i <= N; i += par.nt()) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    double (*st)[4] = reinterpret_cast<double (*)[4]>(sm.M);       // [(N + 1) * 10][4]: a_p, a_d, grad'dz, sum ds/s per item
+    static_assert((NMAX + 1) * 10 * 4 <= MSZ + NX * NZ, "slack step scratch must fit in M | W");
+    for (int t = tid; t < (N + 1) * 10; t += nt) {
+      const int role = t / (N + 1), i = t - role * (N + 1);
+      const bool has_u = i < N;
       const uint64_t mask = sm.mask[i];
-      const double* x = w.X + i * NX; const double* dx = w.DX + i * NX;
+      const double* dx = w.DX + i * NX; const double* du = w.DU + (has_u ? i : 0) * NU;
       const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR; double* ds = w.DS + i * NR;
       const double* rec = w.REC + (size_t)i * RECSZ;
       double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
-      double x_[NX], u_[NU], xp[NX], g[NR], jd[NR];
-      for (int j = 0; j < NX; ++j) x_[j] = x[j];
-      for (int r = 0; r < NR; ++r) jd[r] = 0.0;
-      if (i < N) {
-        const double* u = w.U + i * NU; const double* du = w.DU + i * NU;
-        for (int j = 0; j < NU; ++j) u_[j] = u[j];
-        dyn_step(c, in, i, x_, u_, xp);
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
-        // Lyapunov: gradient in xi-space from the record
-        double dF[3] = {0, 0, 0};
-        for (int v = 0; v < 8; ++v) { const double ge = (v < 4) ? gl : gr; for (int j = 0; j < 3; ++j) dF[j] += ge * du[3 * v + j]; }
-        for (int j = 0; j < 3; ++j)
-          jd[R_LYAP] += rec[Q_LG + j] * dx[IP + j] + rec[Q_LG + 3 + j] * dx[IV + j] + rec[Q_LG + 6 + j] * dx[ITH + j] + rec[Q_LG + 9 + j] * dF[j];
-        if (mask & (1ull << R_HW)) {
-          const double* bav = rec + Q_BA;
-          for (int j = 0; j < 24; ++j) {
-            const int ax = j % 3;
-            jd[R_HW] += 2.0 * (xp[IH + (ax + 1) % 3] * bav[4 * j + 1] + xp[IH + (ax + 2) % 3] * bav[4 * j + 2]) * du[j];
+      auto row = [&](int r, double dsr) {
+        const double sv = s[r], lv = lam[r];
+        ds[r] = dsr;
+        const double dl = -lv + mu / sv - lv / sv * dsr;
+        if (dsr < 0.0) { const double a = -tau * sv / dsr; ap = a < ap ? a : ap; }
+        if (dl < 0.0) { const double a = -tau * lv / dl; ad = a < ad ? a : ad; }
+        dsos += dsr / sv;
+      };
+      if (role < 8) {
+        const int v = role;
+        if (has_u) {
+          const double f0 = du[3 * v], f1 = du[3 * v + 1], f2 = du[3 * v + 2], mf = c.mu_fric;
+          if (mask & (1ull << (R_UNI + v))) {
+            row(R_FRIC + 4 * v + 0, -rec[Q_RG + R_FRIC + 4 * v + 0] - (f0 - mf * f2));
+            row(R_FRIC + 4 * v + 1, -rec[Q_RG + R_FRIC + 4 * v + 1] - (-f0 - mf * f2));
+            row(R_FRIC + 4 * v + 2, -rec[Q_RG + R_FRIC + 4 * v + 2] - (f1 - mf * f2));
+            row(R_FRIC + 4 * v + 3, -rec[Q_RG + R_FRIC + 4 * v + 3] - (-f1 - mf * f2));
+            row(R_UNI + v, -rec[Q_RG + R_UNI + v] - (-f2));
+          } else {
+            for (int q = 0; q < 4; ++q) ds[R_FRIC + 4 * v + q] = 0.0;
+            ds[R_UNI + v] = 0.0;
+          }
+          gd += rec[Q_GC + 3 * v] * f0 + rec[Q_GC + 3 * v + 1] * f1 + rec[Q_GC + 3 * v + 2] * f2;
+        } else {
+          for (int q = 0; q < 4; ++q) ds[R_FRIC + 4 * v + q] = 0.0;
+          ds[R_UNI + v] = 0.0;
+        }
+        gd += rec[Q_GC + 32 + IQ + v] * dx[IQ + v];
+      } else if (role == 8) {
+        // explicit rows: the solve returned the new multiplier w; ds follows from s dlam + lam ds = mu - s lam
+        if (mask & (1ull << R_LYAP)) { const double sv = s[R_LYAP], lv = lam[R_LYAP]; row(R_LYAP, mu / lv - sv - sv / lv * (w.DW[i * NW] - lv)); }
+        else ds[R_LYAP] = 0.0;
+        if (mask & (1ull << R_HW)) { const double sv = s[R_HW], lv = lam[R_HW]; row(R_HW, mu / lv - sv - sv / lv * (w.DW[i * NW + 1] - lv)); }
+        else ds[R_HW] = 0.0;
+        if (mask & (1ull << R_PZ)) row(R_PZ, -rec[Q_RG + R_PZ] - dx[IP + 2]);
+        else ds[R_PZ] = 0.0;
+        for (int j = 0; j < 12; ++j) gd += rec[Q_GC + 32 + j] * dx[j];
+      } else {
+        for (int e = 0; e < 2; ++e) {
+          const bool box = (mask >> (R_BOX + 6 * e)) & 1ull;
+          for (int j = 0; j < 3; ++j) {
+            const int r = R_BOX + 6 * e + 2 * j;
+            const double v = dx[(e ? IPR : IPL) + j];
+            if (box) { row(r, -rec[Q_RG + r] - v); row(r + 1, -rec[Q_RG + r + 1] + v); }
+            else { ds[r] = 0.0; ds[r + 1] = 0.0; }
           }
         }
-        for (int v = 0; v < 8; ++v) {
-          const double* f = du + 3 * v; const double mf = c.mu_fric;
-          jd[R_FRIC + 4 * v + 0] = f[0] - mf * f[2]; jd[R_FRIC + 4 * v + 1] = -f[0] - mf * f[2];
-          jd[R_FRIC + 4 * v + 2] = f[1] - mf * f[2]; jd[R_FRIC + 4 * v + 3] = -f[1] - mf * f[2];
-          jd[R_UNI + v] = -f[2];
-        }
-        for (int j = 0; j < NU; ++j) gd += rec[Q_GC + j] * du[j];
-      } else {
-        for (int j = 0; j < NU; ++j) u_[j] = 0.0;
-        for (int j = 0; j < NX; ++j) xp[j] = x_[j];
+        for (int j = 12; j < 20; ++j) gd += rec[Q_GC + 32 + j] * dx[j];
+        if (has_u) for (int j = 24; j < 32; ++j) gd += rec[Q_GC + j] * du[j];
       }
-      jd[R_PZ] = dx[IP + 2];
-      for (int e = 0; e < 2; ++e)
-        for (int j = 0; j < 3; ++j) { const double v = dx[(e ? IPR : IPL) + j]; jd[R_BOX + 6 * e + 2 * j] = v; jd[R_BOX + 6 * e + 2 * j + 1] = -v; }
-      for (int j = 0; j < NX; ++j) gd += rec[Q_GC + 32 + j] * dx[j];
-      stage_ineq(c, in, i, mask, x_, u_, xp, g);
-      for (int r = 0; r < NR; ++r) {
-        if (!(mask & (1ull << r))) { ds[r] = 0.0; continue; }
-        double dsr = -(g[r] - c.relax + s[r]) - jd[r];
-        if (r == R_LYAP || r == R_HW) {
-          // explicit rows: the solve returned the new multiplier w; ds follows from s dlam + lam ds = mu - s lam
-          const double dlw = w.DW[i * NW + (r == R_HW ? 1 : 0)] - lam[r];
-          dsr = mu / lam[r] - s[r] - s[r] / lam[r] * dlw;
-        }
-        ds[r] = dsr;
-        const double dl = -lam[r] + mu / s[r] - lam[r] / s[r] * dsr;
-        if (dsr < 0.0) { const double a = -tau * s[r] / dsr;
-#ifdef CMPC_TRACE
-          if (cmpc_trace_on > 1 && a < 0.3) printf("      block stage %d row %d a %.3e s %.3e ds %.3e lam %.3e\n", i, r, a, s[r], dsr, lam[r]);
-#endif
-          ap = a < ap ? a : ap; }
-        if (dl < 0.0) { const double a = -tau * lam[r] / dl; ad = a < ad ? a : ad; }
-        dsos += dsr / s[r];
+      st[t][0] = ap; st[t][1] = ad; st[t][2] = gd; st[t][3] = dsos;
+    }
+    par.sync();
+    // two-level reduction: per stage (threads), then over the stages (every thread, broadcast reads)
+    for (int i = tid; i <= N; i += nt) {
+      double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
+      for (int role = 0; role < 10; ++role) {
+        const double* q = st[role * (N + 1) + i];
+        ap = q[0] < ap ? q[0] : ap; ad = q[1] < ad ? q[1] : ad; gd += q[2]; dsos += q[3];
       }
       sm.acc[i][0] = ap; sm.acc[i][1] = ad; sm.acc[i][2] = gd; sm.acc[i][3] = dsos;
     }
@@ -1062,10 +1438,184 @@ struct Solver {
     par.sync();
   }
 
+  // ---- trial point (x + a dx, u + a du, s + a ds) for the line search: constraint violation theta, cost (with and
+  // without the regularisation term), sum ln s, max unrelaxed violation.  CTA-wide like the eval pass.
+#ifdef CMPC_TRIAL_SERIAL
   CMPC_HD void trial(double alpha, double* out) {
     const int N = c.N;
     for (int i = par.tid(); i <= N; i += par.nt()) stage_trial(c, in, w, i, sm.mask[i], alpha, sm.acc[i]);
     par.sync();
+    reduce_trial(out);
+  }
+#else
+  CMPC_HD void trial(double alpha, double* out) {
+    const int N = c.N, tid = par.tid(), nt = par.nt();
+    TrialScratch* ts = reinterpret_cast<TrialScratch*>(sm.M);
+    const double d = c.delta, m = in.mass, k1 = in.k1;
+    for (int i0 = 0; i0 <= N; i0 += TCH) {
+      const int ns = (N + 1 - i0) < TCH ? (N + 1 - i0) : TCH;
+      for (int t = tid; t < ns * 2; t += nt) {
+        const int il = t >> 1, e = t & 1, i = i0 + il, o = i * NX + (e ? IPSR : IPSL);
+        const double psi = w.X[o] + alpha * w.DX[o];
+        ts[il].cs[e] = cos(psi); ts[il].sn[e] = sin(psi);
+      }
+      par.sync();
+      for (int t = tid; t < ns * 8; t += nt) {
+        const int il = t >> 3, v = t & 7, i = i0 + il;
+        if (i >= N) continue;
+        const int e = v >> 2, k = v & 3;
+        const double* X = w.X + i * NX; const double* DX = w.DX + i * NX;
+        const double* U = w.U + i * NU; const double* DU = w.DU + i * NU;
+        const int po = e ? IPR : IPL;
+        const double cs = ts[il].cs[e], sn = ts[il].sn[e];
+        double cx, cy; corner(c, k, cx, cy);
+        const double rx = cs * cx - sn * cy, ry = sn * cx + cs * cy;
+        const double p0 = X[0] + alpha * DX[0], p1 = X[1] + alpha * DX[1], p2 = X[2] + alpha * DX[2];
+        const double r0 = rx + X[po] + alpha * DX[po] - p0, r1 = ry + X[po + 1] + alpha * DX[po + 1] - p1, r2 = X[po + 2] + alpha * DX[po + 2] - p2;
+        const double f0 = U[3 * v] + alpha * DU[3 * v], f1 = U[3 * v + 1] + alpha * DU[3 * v + 1], f2 = U[3 * v + 2] + alpha * DU[3 * v + 2];
+        double* p = ts[il].part[v];
+        p[0] = f0; p[1] = f1; p[2] = f2;
+        p[3] = r1 * f2 - r2 * f1; p[4] = r2 * f0 - r0 * f2; p[5] = r0 * f1 - r1 * f0;
+        p[6] = f0 * f0 + f1 * f1 + f2 * f2;
+      }
+      par.sync();
+      for (int t = tid; t < ns * 11; t += nt) {
+        const int il = t / 11, q = t - il * 11, i = i0 + il;
+        if (i >= N) continue;
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double (*pt)[7] = ts[il].part;
+        double s = 0.0;
+        if (q < 6) { const int e = q / 3, j = q - 3 * e; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][j]; }
+        else if (q < 9) { const int j = q - 6; for (int v = 0; v < 8; ++v) s += (v < 4 ? gl : gr) * pt[v][3 + j]; }
+        else { const int e = q - 9; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][6]; }
+        ts[il].sum[q] = s;
+      }
+      par.sync();
+      for (int t = tid; t < ns * 10; t += nt) {
+        const int role = t / ns, il = t - role * ns, i = i0 + il;
+        const bool has_u = i < N;
+        TrialScratch& E = ts[il];
+        const double* X = w.X + i * NX; const double* DX = w.DX + i * NX;
+        const double* U = w.U + (has_u ? i : 0) * NU; const double* DU = w.DU + (has_u ? i : 0) * NU;
+        const double* Xn = w.X + (has_u ? i + 1 : i) * NX; const double* DXn = w.DX + (has_u ? i + 1 : i) * NX;
+        const double* S = w.S + i * NR; const double* DS = w.DS + i * NR;
+        const uint64_t mask = sm.mask[i];
+        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        double theta = 0.0, cost = 0.0, cref = 0.0, lns = 0.0, viol = 0.0;
+        auto row = [&](int r, double g) {
+          const double st = S[r] + alpha * DS[r];
+          theta += fabs(g - c.relax + st); lns += log(st); viol = g > viol ? g : viol;
+        };
+        auto defect = [&](int r, double xp) {
+          const double ad = fabs(xp - (Xn[r] + alpha * DXn[r]));
+          theta += ad; viol = ad > viol ? ad : viol;
+        };
+        if (role < 8) {
+          if (has_u) {
+            const int v = role, e = v >> 2;
+            const double ge = e ? gr : gl, mf = c.mu_fric;
+            const double* p = E.part[v];
+            const double f0 = p[0], f1 = p[1], f2 = p[2];
+            if (mask & (1ull << (R_UNI + v))) {
+              row(R_FRIC + 4 * v + 0, f0 - mf * f2); row(R_FRIC + 4 * v + 1, -f0 - mf * f2);
+              row(R_FRIC + 4 * v + 2, f1 - mf * f2); row(R_FRIC + 4 * v + 3, -f1 - mf * f2);
+              row(R_UNI + v, -f2);
+            }
+            cost += (ge * c.w_sym + (1.0 - ge) * c.w_swing) * p[6];
+            if (i >= 1) {
+              const double dz = f2 - (X[IQ + v] + alpha * DX[IQ + v]);
+              cost += c.w_rate * in.gamma[2 * (i - 1) + e] * dz * dz;
+            }
+            cref = cost;
+            defect(IQ + v, f2);
+          }
+        } else if (role == 8) {
+          double x[12];
+#pragma unroll
+          for (int j = 0; j < 12; ++j) x[j] = X[j] + alpha * DX[j];
+          if (i >= 1) {
+            const double* ref = in.com_ref + 9 * (i - 1);
+            cost += c.w_xy * ((x[0] - ref[0]) * (x[0] - ref[0]) + (x[1] - ref[1]) * (x[1] - ref[1])) + wz_of(c, i - 1) * (x[2] - ref[2]) * (x[2] - ref[2]);
+          }
+          if (mask & (1ull << R_PZ)) row(R_PZ, x[IP + 2] - c.pz_max);
+          if (has_u) {
+            const double* ref = in.com_ref + 9 * i;
+            double F[3], xph[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { F[j] = gl * E.sum[j] + gr * E.sum[3 + j]; xph[j] = x[IH + j] + d * E.sum[6 + j]; }
+            cost += c.w_h * (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]);
+            // symmetry term: w_sym (sum |f_k|^2 - 4 |mean|^2) per stance foot; the first part is with the vertices
+            cost -= gl * c.w_sym * 0.25 * (E.sum[0] * E.sum[0] + E.sum[1] * E.sum[1] + E.sum[2] * E.sum[2]);
+            cost -= gr * c.w_sym * 0.25 * (E.sum[3] * E.sum[3] + E.sum[4] * E.sum[4] + E.sum[5] * E.sum[5]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              defect(IP + j, x[IP + j] + d * x[IV + j]);
+              defect(IV + j, x[IV + j] + d * ((j == 2 ? -c.grav : 0.0) + F[j] / m));
+              defect(IH + j, xph[j]);
+              defect(ITH + j, x[ITH + j] + (d / m) * (k1 * (x[IP + j] - ref[j]) + x[IV + j] - ref[3 + j]));
+            }
+            if (mask & (1ull << R_LYAP)) {
+              double q = 0.0;
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double grav = (j == 2) ? -c.grav : 0.0;
+                const double vp = x[IV + j] + d * (grav + F[j] / m);
+                const double z1 = x[IP + j] + d * x[IV + j] - ref[j];
+                const double z2 = k1 * z1 + vp - ref[3 + j];
+                const double ae = F[j] / m + grav - ref[6 + j] + x[ITH + j] / m;
+                q += -k1 * z1 * z1 + k1 * z2 * z2 + (1.0 - k1 * k1) * z1 * z2 + z2 * ae;
+              }
+              row(R_LYAP, q);
+            }
+            if (mask & (1ull << R_HW))
+              row(R_HW, xph[0] * xph[0] + xph[1] * xph[1] + xph[2] * xph[2] - (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]));
+          }
+          cref = cost;
+        } else {
+          const double* fr = in.foot_ref + 8 * (i >= 1 ? i - 1 : 0);
+          double creg = 0.0;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double ge = e ? gr : gl;
+            const int po = e ? IPSR : IPSL, xo = e ? IPR : IPL;
+            const bool box = (i >= 1) && ((mask >> (R_BOX + 6 * e)) & 1ull);
+            const double psi = X[po] + alpha * DX[po];
+            if (i >= 1) cost += c.w_foot * ge * (psi - fr[6 + e]) * (psi - fr[6 + e]);
+            if (has_u) { const double uv = U[30 + e] + alpha * DU[30 + e]; defect(po, psi + d * (1.0 - ge) * uv); creg += c.eps_reg * uv * uv; }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const double xv = X[xo + j] + alpha * DX[xo + j];
+              if (i >= 1) {
+                const double err = xv - fr[3 * e + j];
+                cost += c.w_foot * ge * err * err;
+                if (box) { row(R_BOX + 6 * e + 2 * j, err - c.box[j]); row(R_BOX + 6 * e + 2 * j + 1, -err - c.box[j]); }
+              }
+              if (has_u) { const double uv = U[24 + 3 * e + j] + alpha * DU[24 + 3 * e + j]; defect(xo + j, xv + d * (1.0 - ge) * uv); creg += c.eps_reg * uv * uv; }
+            }
+          }
+          cref = cost; cost += creg;
+        }
+        double* st = E.st[role];
+        st[0] = theta; st[1] = cost; st[2] = lns; st[3] = viol; st[4] = cref;
+      }
+      par.sync();
+      for (int il = tid; il < ns; il += nt) {
+        double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
+        for (int r = 0; r < 10; ++r) {
+          const double* q = ts[il].st[r];
+          theta += q[0]; cost += q[1]; lns += q[2]; viol = q[3] > viol ? q[3] : viol; cref += q[4];
+        }
+        double* a = sm.acc[i0 + il];
+        a[0] = theta; a[1] = cost; a[2] = lns; a[3] = viol; a[4] = cref;
+      }
+      par.sync();
+    }
+    reduce_trial(out);
+  }
+#endif
+
+  CMPC_HD void reduce_trial(double* out) {
+    const int N = c.N;
     double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
     for (int i = 0; i <= N; ++i) {
       theta += sm.acc[i][0]; cost += sm.acc[i][1]; lns += sm.acc[i][2];
@@ -1105,6 +1655,7 @@ struct Solver {
       }
       sm.csr_ptr[NX] = (short)n;
     }
+    if (par.tid() == 0) lyapunov_consts(c, in, sm.lyapC);
     for (int sl = 0; sl < Par::TPT; ++sl) {
       const int tile = par.tid() + sl * par.nt();                   // tile (ti, tj), ti >= tj >= 1, row-major in the triangle
       int ti = 0;

@@ -58,6 +58,65 @@ int hostsim_stage_debug(int N, const double* x0, const double* com_ref, const do
   return 0;
 }
 
+// Debug: the CTA-wide eval pass against the thread-per-stage reference evaluation (stage_derivs) at the iterate stored in
+// `work`.  out[0] = max relative difference over all record entries, out[1] = same over the per-stage statistics.
+int hostsim_eval_compare(int N, const double* x0, const double* com_ref, const double* foot_ref, const double* gamma,
+                         double mass, double k1, double* work, double* out) {
+  Config c = default_config(N);
+  Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
+  Work w = carve_work(work, N);
+  Smem* sm = new Smem();
+  ParSerial par;
+  Solver<ParSerial> sol(c, in, w, *sm, par);
+  double pv; build_masks(c, in, sm->mask, &pv);
+  lyapunov_consts(c, in, sm->lyapC);
+  double ev[8];
+  sol.eval(ev);
+  std::vector<double> rec_new(w.REC, w.REC + (size_t)(N + 1) * RECSZ);
+  std::vector<double> acc_new((N + 1) * 8);
+  for (int i = 0; i <= N; ++i) for (int q = 0; q < 5; ++q) acc_new[i * 8 + q] = sm->acc[i][q];
+  for (size_t t = 0; t < rec_new.size(); ++t) w.REC[t] = 0.0;
+  double e_rec = 0.0, e_acc = 0.0;
+  for (int i = 0; i <= N; ++i) {
+    double acc[8];
+    stage_derivs(c, in, w, i, sm->mask[i], 0.0, acc);
+    for (int t = 0; t < RECSZ; ++t) {
+      if (t >= 597 && t < 600) continue;                         // unused slots
+      if (i == N && !((t >= Q_GC + 32 && t < Q_GC + 60) || (t >= Q_M1 + 32 && t < Q_M1 + 60) || (t >= Q_M2 + 32 && t < Q_M2 + 60) || (t >= Q_DIAG + 32 && t < Q_DIAG + 60))) continue;
+      if ((t == Q_HRG || (t >= Q_HP && t < Q_HP + 3)) && !(sm->mask[i] & (1ull << R_HW))) continue;   // read at stage 0 only
+      const double a = w.REC[(size_t)i * RECSZ + t], b = rec_new[(size_t)i * RECSZ + t];
+      const double e = fabs(a - b) / (1.0 + fabs(a));
+      if (e > e_rec) { e_rec = e; out[2] = i; out[3] = t; out[4] = a; out[5] = b; }
+    }
+    for (int q = 0; q < 5; ++q) {
+      const double a = acc[q], b = acc_new[i * 8 + q];
+      const double e = fabs(a - b) / (1.0 + fabs(a));
+      if (e > e_acc) { e_acc = e; out[6] = i; out[7] = q; }
+    }
+  }
+  out[0] = e_rec; out[1] = e_acc;
+  // trial pass at a step of 0.37 along a pseudo-random direction against the per-stage evaluation
+  {
+    unsigned long long seed = 88172645463325252ull;
+    auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return (double)(seed % 2000001) / 1e6 - 1.0; };
+    for (int t = 0; t < (N + 1) * NX; ++t) w.DX[t] = 1e-3 * rnd();
+    for (int t = 0; t < N * NU; ++t) w.DU[t] = 1e-1 * rnd();
+    for (int t = 0; t < (N + 1) * NR; ++t) w.DS[t] = 0.3 * w.S[t] * rnd();
+    double tr[5], ref[5] = {0, 0, 0, 0, 0};
+    sol.trial(0.37, tr);
+    for (int i = 0; i <= N; ++i) {
+      double a[8];
+      stage_trial(c, in, w, i, sm->mask[i], 0.37, a);
+      ref[0] += a[0]; ref[1] += a[1]; ref[2] += a[2]; ref[3] = a[3] > ref[3] ? a[3] : ref[3]; ref[4] += a[4];
+    }
+    double e = 0.0;
+    for (int q = 0; q < 5; ++q) { const double v = fabs(tr[q] - ref[q]) / (1.0 + fabs(ref[q])); e = v > e ? v : e; }
+    out[8] = e;
+  }
+  delete sm;
+  return 0;
+}
+
 int hostsim_solve(int N, const double* x0, const double* com_ref, const double* foot_ref, const double* gamma,
                   double mass, double k1, const double* cfg_over, int warm, double* work, double* stats_out) {
   Config c = default_config(N);

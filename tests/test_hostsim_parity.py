@@ -73,3 +73,24 @@ def test_analytic_stage_hessian_against_finite_differences(golden):
             wp[idx] += h; wm[idx] -= h
             H[:, j] = (dbg(wp, i)[0] - dbg(wm, i)[0]) / (2 * h)
         assert np.abs(H - M).max() <= 1e-5 * max(1.0, np.abs(M).max()), i
+
+
+def test_wide_eval_pass_matches_thread_per_stage_evaluation(golden):
+    """The CTA-wide eval and trial passes (stage x role work items) give the same derivative record, statistics and merit
+    quantities as the plain thread-per-stage evaluations they replaced, at mid-solve iterates of standing, swing and
+    landing ticks."""
+    for N in (10, 20):
+        g = golden[N]
+        for tick in (0, 262, 230):
+            if tick not in list(g["ticks"]):
+                continue
+            k = list(g["ticks"]).index(tick)
+            prob = problem(g, k, N)
+            r = hostsim.solve(prob, max_iter=6)
+            L = hostsim.lib()
+            x0, com, foot, gam = hostsim.pack(prob)
+            dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            out = np.zeros(9)
+            L.hostsim_eval_compare(ctypes.c_int(N), dp(x0), dp(com), dp(foot), dp(gam), ctypes.c_double(prob.mass),
+                                   ctypes.c_double(prob.k1), dp(r["work"]), dp(out))
+            assert out[0] <= 1e-10 and out[1] <= 1e-9 and out[8] <= 1e-10, (N, tick, out)     # summation order differs
