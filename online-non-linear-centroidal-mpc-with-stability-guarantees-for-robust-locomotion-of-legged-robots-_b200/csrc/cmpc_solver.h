@@ -103,17 +103,14 @@ struct Smem {
   double P[NX * NX];         // cost-to-go Hessian of stage i+1 (full symmetric)
   double pv[NX];             // cost-to-go gradient
   double tv[NX];             // p + P d
-  double bav[NZ * 4];        // sparse [B A] values of the current stage
-  double rec[RECSZ - Q_D];   // rest of the current record (d, diag, friction, Lyapunov, ...)
-  double dxs[NX], dxn[NX], zs[NA];
-  double colbuf[2 * 64];     // pivot column, double buffered
-  double panel[16 * PSTR];   // 64 x 4 panel of L (one tile column) as 16 tile rows of 16 values
+  double recb[2][Q_RG];      // derivative record of the current stage and, arriving asynchronously, of the next one to be assembled
+  double zs[NA];
   double dpub[10];           // factored diagonal tile: reciprocal diagonal (4) and strict lower part (6)
   double rdiag[NA];          // reciprocal of the stored diagonal of L
   double lyapC[16];          // curvature of the Lyapunov row in (p, v, theta, F) space (per instance)
-  double red[40];
+  double red[2];
   uint64_t mask[NMAX + 1];
-  double acc[NMAX + 1][8];   // per-stage partial results of eval / trial passes
+  double acc[NMAX + 1][5];   // per-stage partial results of the eval / slack-step / trial passes
   int flag;
   long long prof[PF_COUNT];
   short csr_ptr[NX + 1];      // structural pattern of [B A] by rows (gather form)
@@ -476,14 +473,6 @@ struct Solver {
   // from the trial pass).  CTA-wide: work items are (stage, role) pairs -- 8 vertex roles (friction rows, force columns),
   // a CoM role (p, v, h, theta) and a feet role (foot poses, foot inputs) -- in short barrier-separated phases, all
   // temporaries in registers or in the per-stage scratch: no per-thread arrays.
-#ifdef CMPC_EVAL_SERIAL
-  CMPC_HD void eval(double* out) {
-    const int N = c.N;
-    for (int i = par.tid(); i <= N; i += par.nt()) stage_derivs(c, in, w, i, sm.mask[i], mu, sm.acc[i]);
-    par.sync();
-    reduce_acc(out);
-  }
-#else
   CMPC_HD static void stat_row(double* st, double rg, double s, double lam) {
     const double ar = fabs(rg), sl = s * lam;
     st[0] = ar > st[0] ? ar : st[0]; st[2] = sl > st[2] ? sl : st[2]; st[3] = sl < st[3] ? sl : st[3]; st[4] += lam;
@@ -807,25 +796,24 @@ struct Solver {
           msum += q[4];
         }
         double* a = sm.acc[i0 + il];
-        a[0] = prim; a[1] = dual; a[2] = smax; a[3] = smin; a[4] = msum; a[5] = 0.0; a[6] = 0.0; a[7] = 0.0;
+        a[0] = prim; a[1] = dual; a[2] = smax; a[3] = smin; a[4] = msum;
       }
       par.sync();
     }
     reduce_acc(out);
   }
-#endif
 
   // tiny reduction over <= 65 stages done redundantly by every thread (broadcast reads)
   CMPC_HD void reduce_acc(double* out) {
     const int N = c.N;
-    double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0, cost = 0, theta = 0, lns = 0;
+    double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0;
     for (int i = 0; i <= N; ++i) {
       const double* a = sm.acc[i];
       prim = a[0] > prim ? a[0] : prim; dual = a[1] > dual ? a[1] : dual;
       smax = a[2] > smax ? a[2] : smax; smin = a[3] < smin ? a[3] : smin;
-      ssum += a[4]; cost += a[5]; theta += a[6]; lns += a[7];
+      ssum += a[4];
     }
-    out[0] = prim; out[1] = dual; out[2] = smax; out[3] = smin; out[4] = ssum; out[5] = cost; out[6] = theta; out[7] = lns;
+    out[0] = prim; out[1] = dual; out[2] = smax; out[3] = smin; out[4] = ssum; out[5] = 0.0; out[6] = 0.0; out[7] = 0.0;
     par.sync();
   }
 
@@ -857,17 +845,33 @@ struct Solver {
   // cancellation, so their new multipliers w stay explicit unknowns of the (quasi-definite) stage block:
   //   [ H   g ] [dz]   [ -grad          ]
   //   [ g' -1/sigma ] [w ] = [ -(r_g + mu/lam) ]
-  CMPC_HD void assemble_stage(int i, double reg) {
+  // R: the stage's derivative record staged in shared memory (R[Q_xxx]).  Five barriers: the phases between them write
+  // disjoint sets of entries.  The products W = P [B A] and tv = p + P d of the cost-to-go term are formed alongside
+  // the first phase (they do not touch M).
+  CMPC_HD void assemble_stage(int i, double reg, const double* R) {
     const int tid = par.tid(), nt = par.nt();
-    const double* rec = w.REC + (size_t)i * RECSZ;
-    for (int t = tid; t < NZ * 4; t += nt) sm.bav[t] = rec[Q_BA + t];
-    for (int t = tid; t < RECSZ - Q_D; t += nt) sm.rec[t] = rec[Q_D + t];
+    const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
+    const double* bav = R + Q_BA;
     for (int t = tid; t < MSZ; t += nt) sm.M[t] = 0.0;
+    // W = P [B A]  (28 x 60): warp per row r, lanes over columns j;  tv = p + P d
+    for (int r = wid; r < NX; r += nw) {
+      const double* Pr = sm.P + r * NX;
+      for (int j = lane; j < NZ; j += nl) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int rr = sm.barow[4 * j + q]; if (rr >= 0) s += Pr[rr] * bav[4 * j + q]; }
+        sm.W[r * NZ + j] = s;
+      }
+    }
+    for (int r = tid; r < NX; r += nt) {
+      double s = sm.pv[r];
+      for (int j = 0; j < NX; ++j) s += sm.P[r * NX + j] * R[Q_D + j];
+      sm.tv[r] = s;
+    }
     par.sync();
-    const double* R = sm.rec - Q_D;             // R[Q_xxx] addresses the staged record
     const bool has_hw = (i == 0) && (sm.mask[0] & (1ull << R_HW));
     for (int t = tid; t < NZ; t += nt) {
-      sm.M[mi(GR, mz(t))] = rec[Q_GC + t] + mu * rec[Q_M1 + t] + rec[Q_M2 + t];
+      sm.M[mi(GR, mz(t))] = R[Q_GC + t] + mu * R[Q_M1 + t] + R[Q_M2 + t];
       sm.M[mi(mz(t), mz(t))] = R[Q_DIAG + t] + reg;
     }
     if (tid == 0) {
@@ -877,72 +881,47 @@ struct Solver {
       sm.M[mi(GR, NU + 1)] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
     }
     par.sync();
-    // friction barrier blocks (lower triangle)
-    for (int t = tid; t < 48; t += nt) {
-      const int v = t / 6, e6 = t % 6;
-      const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
-      const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
-      sm.M[mi(3 * v + rr, 3 * v + cc)] += R[Q_FRIC + t];
-    }
-    par.sync();
-    // symmetry-term off-diagonals (-2 w_sym / 4 between same-axis components of one foot) and rate cross terms
-    for (int t = tid; t < 36 + 8; t += nt) {
-      if (t < 36) {
-        const int e = t / 18, ax = (t % 18) / 6, pr = t % 6;
+    // friction barrier blocks (lower triangle, within a vertex) | symmetry-term off-diagonals (-2 w_sym / 4 between
+    // same-axis components of two vertices of one foot) | rate cross terms (q_v, f_z): disjoint entries
+    for (int t = tid; t < 48 + 36 + 8; t += nt) {
+      if (t < 48) {
+        const int v = t / 6, e6 = t % 6;
+        const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
+        const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
+        sm.M[mi(3 * v + rr, 3 * v + cc)] += R[Q_FRIC + t];
+      } else if (t < 48 + 36) {
+        const int q = t - 48, e = q / 18, ax = (q % 18) / 6, pr = q % 6;
         const int ka[6] = {1, 2, 2, 3, 3, 3}, kb[6] = {0, 0, 1, 0, 1, 2};
         sm.M[mi(12 * e + 3 * ka[pr] + ax, 12 * e + 3 * kb[pr] + ax)] += -0.5 * c.w_sym * R[Q_GAM + e];
       } else {
-        const int v = t - 36;
+        const int v = t - 84;
         sm.M[mi(XO + IQ + v, 3 * v + 2)] += -2.0 * R[Q_GAMP + v / 4];
       }
     }
     par.sync();
-    // Lyapunov row: lam * C (x) I_3 curvature over the 33 touched variables, and its gradient as row/column NU.
-    // Touched variable a (0..32): forces 0..23 (type F, scaled by gamma_e), then p, v, theta.
-    {
-      const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
-      for (int ai = wid; ai < 33; ai += nw) {
-        int ma, ta, xa; double sa;
-        if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
-        else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
-        if (lane == 0) {
-          const double gv = sa * R[Q_LG + 3 * ta + xa];
-          if (ma < NU) sm.M[mi(NU, ma)] = gv; else sm.M[mi(ma, NU)] = gv;
-        }
-        if (sa == 0.0) continue;
-        // same-axis partners only: bi = xa, xa + 3, ... (forces and states keep the axis in the low index)
-        for (int bq = lane; 3 * bq + xa <= ai; bq += nl) {
-          const int bi = 3 * bq + xa;
-          int mb, tb; double sb;
-          if (bi < 24) { mb = bi; tb = 3; sb = R[Q_GAM + bi / 12]; }
-          else { const int q = bi - 24; tb = q / 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xa; }
-          const double v = sa * sb * R[Q_LC + 4 * ta + tb];
-          if (ma >= mb) sm.M[mi(ma, mb)] += v; else sm.M[mi(mb, ma)] += v;
-        }
+    // Lyapunov row: lam * C (x) I_3 curvature over the 33 touched variables (same-axis pairs), and its gradient as
+    // row/column NU.  Touched variable a (0..32): forces 0..23 (type F, scaled by gamma_e), then p, v, theta.
+    for (int ai = wid; ai < 33; ai += nw) {
+      int ma, ta, xa; double sa;
+      if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
+      else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
+      if (lane == 0) {
+        const double gv = sa * R[Q_LG + 3 * ta + xa];
+        if (ma < NU) sm.M[mi(NU, ma)] = gv; else sm.M[mi(ma, NU)] = gv;
+      }
+      if (sa == 0.0) continue;
+      // same-axis partners only: bi = xa, xa + 3, ... (forces and states keep the axis in the low index)
+      for (int bq = lane; 3 * bq + xa <= ai; bq += nl) {
+        const int bi = 3 * bq + xa;
+        int mb, tb; double sb;
+        if (bi < 24) { mb = bi; tb = 3; sb = R[Q_GAM + bi / 12]; }
+        else { const int q = bi - 24; tb = q / 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xa; }
+        const double v = sa * sb * R[Q_LC + 4 * ta + tb];
+        if (ma >= mb) sm.M[mi(ma, mb)] += v; else sm.M[mi(mb, ma)] += v;
       }
     }
-    par.sync();
-    // angular-momentum row (stage 0): curvature 2 lam Bh'Bh in the force block, gradient as row NU+1
-    if (has_hw) {
-      const double lamh = R[Q_HLAM];
-      for (int t = tid; t < 24 * 24 + 24; t += nt) {
-        if (t >= 24 * 24) {
-          const int a_ = t - 24 * 24;
-          double ca[3] = {0, 0, 0};
-          ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
-          sm.M[mi(NU + 1, a_)] = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
-          continue;
-        }
-        const int a_ = t / 24, b_ = t % 24;
-        if (b_ > a_) continue;
-        double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
-        ca[(a_ % 3 + 1) % 3] = sm.bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = sm.bav[4 * a_ + 2];
-        cb[(b_ % 3 + 1) % 3] = sm.bav[4 * b_ + 1]; cb[(b_ % 3 + 2) % 3] = sm.bav[4 * b_ + 2];
-        sm.M[mi(a_, b_)] += 2.0 * lamh * (ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2]);
-      }
-      par.sync();
-    }
-    // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u)
+    // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u); cross-axis pairs only, so
+    // no entry is shared with the Lyapunov curvature above
     {
       const double y0 = R[Q_YH], y1 = R[Q_YH + 1], y2 = R[Q_YH + 2];      // delta * y_h
       const double Yx[3][3] = {{0, -y2, y1}, {y2, 0, -y0}, {-y1, y0, 0}};
@@ -951,6 +930,7 @@ struct Solver {
         const double ge = R[Q_GAM + e];
         if (q < 18) {
           const int a_ = (q % 9) / 3, b_ = q % 3;
+          if (a_ == b_) continue;
           const double val = ge * Yx[a_][b_];
           if (q < 9) sm.M[mi(XO + IP + b_, 3 * v + a_)] += -val;
           else sm.M[mi(XO + (e ? IPR : IPL) + b_, 3 * v + a_)] += val;
@@ -963,6 +943,32 @@ struct Solver {
       }
     }
     par.sync();
+    // angular-momentum row (stage 0): curvature 2 lam Bh'Bh in the force block, gradient as row NU+1
+    if (has_hw) {
+      const double lamh = R[Q_HLAM];
+      for (int t = tid; t < 24 * 24 + 24; t += nt) {
+        if (t >= 24 * 24) {
+          const int a_ = t - 24 * 24;
+          double ca[3] = {0, 0, 0};
+          ca[(a_ % 3 + 1) % 3] = bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = bav[4 * a_ + 2];
+          sm.M[mi(NU + 1, a_)] = 2.0 * (ca[0] * R[Q_HP] + ca[1] * R[Q_HP + 1] + ca[2] * R[Q_HP + 2]);
+          continue;
+        }
+        const int a_ = t / 24, b_ = t % 24;
+        if (b_ > a_) continue;
+        double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+        ca[(a_ % 3 + 1) % 3] = bav[4 * a_ + 1]; ca[(a_ % 3 + 2) % 3] = bav[4 * a_ + 2];
+        cb[(b_ % 3 + 1) % 3] = bav[4 * b_ + 1]; cb[(b_ % 3 + 2) % 3] = bav[4 * b_ + 2];
+        sm.M[mi(a_, b_)] += 2.0 * lamh * (ca[0] * cb[0] + ca[1] * cb[1] + ca[2] * cb[2]);
+      }
+      par.sync();
+    }
+  }
+
+  // asynchronous copy of stage i's derivative record (without the row residuals) into a staging buffer
+  CMPC_HD void record_in(int i, double* buf) {
+    par.copy_async(buf, w.REC + (size_t)i * RECSZ, Q_RG);
+    par.commit_async();
   }
 
   // ---- backward Riccati sweep.  Returns false if a pivot has the wrong sign (inputs > 0, multipliers < 0).
@@ -973,6 +979,7 @@ struct Solver {
   CMPC_HD bool backward(double reg) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
     const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
+    par.wait_async();                                              // (a sweep abandoned on a bad pivot may have left a record copy in flight)
     {   // terminal stage: P_N diagonal, p_N = modified gradient (x part)
       const double* rec = w.REC + (size_t)N * RECSZ;
       for (int t = tid; t < NX * NX; t += nt) sm.P[t] = 0.0;
@@ -983,34 +990,23 @@ struct Solver {
       }
       par.sync();
     }
+    record_in(N - 1, sm.recb[(N - 1) & 1]);
     for (int i = N - 1; i >= 0; --i) {
       double* fac = w.FAC + (size_t)i * FACSZ;
       CMPC_TIC(sm);
-      assemble_stage(i, reg);
+      par.wait_async();
+      par.sync();                                                  // record i is in; every thread is done with stage i + 1
+      if (i > 0) record_in(i - 1, sm.recb[(i - 1) & 1]);           // lands while stage i is assembled and factorised
+      const double* R = sm.recb[i & 1];
+      const double* bav = R + Q_BA;
+      assemble_stage(i, reg, R);
       CMPC_TOC(sm, PF_ASM);
-      const double* R = sm.rec - Q_D;
-      // W = P [B A]  (28 x 60): warp per row r, lanes over columns j;  tv = p + P d
-      for (int r = wid; r < NX; r += nw) {
-        const double* Pr = sm.P + r * NX;
-        for (int j = lane; j < NZ; j += nl) {
-          double s = 0.0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { const int rr = sm.barow[4 * j + q]; if (rr >= 0) s += Pr[rr] * sm.bav[4 * j + q]; }
-          sm.W[r * NZ + j] = s;
-        }
-      }
-      for (int r = tid; r < NX; r += nt) {
-        double s = sm.pv[r];
-        for (int j = 0; j < NX; ++j) s += sm.P[r * NX + j] * R[Q_D + j];
-        sm.tv[r] = s;
-      }
-      par.sync();
       // M += [B A]' W (lower triangle), gradient row += [B A]' tv : warp per row a, lanes over b <= a
       for (int a_ = wid; a_ <= NZ; a_ += nw) {
         if (a_ < NZ) {
           int rr[4]; double bv[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { rr[q] = sm.barow[4 * a_ + q]; bv[q] = sm.bav[4 * a_ + q]; }
+          for (int q = 0; q < 4; ++q) { rr[q] = sm.barow[4 * a_ + q]; bv[q] = bav[4 * a_ + q]; }
           if (rr[0] < 0) continue;                               // structurally empty column (previous-f_z states)
           double* Mr = sm.M + mi(mz(a_), 0);
           for (int b_ = lane; b_ <= a_; b_ += nl) {
@@ -1023,7 +1019,7 @@ struct Solver {
           for (int b_ = lane; b_ < NZ; b_ += nl) {
             double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const int r2 = sm.barow[4 * b_ + q]; if (r2 >= 0) s += sm.bav[4 * b_ + q] * sm.tv[r2]; }
+            for (int q = 0; q < 4; ++q) { const int r2 = sm.barow[4 * b_ + q]; if (r2 >= 0) s += bav[4 * b_ + q] * sm.tv[r2]; }
             sm.M[mi(GR, mz(b_))] += s;
           }
         }
@@ -1039,6 +1035,7 @@ struct Solver {
       //   2. the owners of the tiles below it form their rows of L (4 x 4 forward substitution, registers) and
       //      publish the 64 x 4 panel                                                         -- barrier B
       //   3. every tile to the right applies the rank-4 update (64 FMAs fed by 32 shared loads).
+      // (the panel and the pivot-column buffer live in the W storage, idle between the P [B A] products and the gains.)
       // The two explicit multipliers (columns 32, 33; pivot sign -1) follow column by column.  The gradient row
       // (row 62) is carried along.  Inputs without coupling at a stage (stance-foot velocities, swing-foot
       // tangential forces) need no special case: their columns are zero below the diagonal.
@@ -1087,7 +1084,7 @@ struct Solver {
         auto panel_tile = [&](double* t, int ti) {
           const double* d = sm.dpub;
           const double i0 = d[0], i1 = d[1], i2 = d[2], i3 = d[3], l10 = d[4], l20 = d[5], l21 = d[6], l30 = d[7], l31 = d[8], l32 = d[9];
-          double* pl = sm.panel + PSTR * ti;
+          double* pl = (sm.W + 128) + PSTR * ti;
 #pragma unroll
           for (int a_ = 0; a_ < 4; ++a_) {
             const double v0 = t[4 * a_] * i0;
@@ -1150,7 +1147,7 @@ struct Solver {
           for (int sl = 0; sl < Par::TPT; ++sl) {
             const int ti = ti_[sl], tj = tj_[sl];
             if (tj <= tk) continue;                                  // (no tile: tj = 0) tiles left of / in the block: final
-            const double* pr = sm.panel + PSTR * ti;
+            const double* pr = (sm.W + 128) + PSTR * ti;
             if (ti == tj) {
               double lr[16];
 #pragma unroll
@@ -1161,7 +1158,7 @@ struct Solver {
                 for (int b_ = 0; b_ <= a_; ++b_)
                   T[sl][4 * a_ + b_] -= lr[4 * a_] * lr[4 * b_] + lr[4 * a_ + 1] * lr[4 * b_ + 1] + lr[4 * a_ + 2] * lr[4 * b_ + 2] + lr[4 * a_ + 3] * lr[4 * b_ + 3];
             } else {
-              const double* pc = sm.panel + PSTR * tj;
+              const double* pc = (sm.W + 128) + PSTR * tj;
               double lr[16];
 #pragma unroll
               for (int q = 0; q < 16; ++q) lr[q] = pr[q];
@@ -1183,7 +1180,7 @@ struct Solver {
           for (int kk = 0; kk < NW; ++kk) {                         // kk static: tiles stay in registers
             const int k = 4 * tk + kk;
             if (!okp) break;
-            double* cb = sm.colbuf + (nproc & 1) * 64;
+            double* cb = sm.W + (nproc & 1) * 64;
             ++nproc;
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl)
@@ -1296,7 +1293,7 @@ struct Solver {
     const int N = c.N, tid = par.tid(), nt = par.nt();
     double* dxall = sm.M;                                        // dx of all stages, (N + 1) x NX: the stage block is idle here
     double* kbuf[2] = {sm.W, sm.W + FWDBUF};                     // W | P storage (contiguous, idle here)
-    double* bbuf[2] = {sm.bav, sm.W + 2 * FWDBUF};
+    double* bbuf[2] = {sm.recb[0], sm.W + 2 * FWDBUF};
     static_assert(2 * FWDBUF + NZ * 4 <= NX * NZ + NX * NX, "forward staging must fit in W | P");
     static_assert((NMAX + 1) * NX <= MSZ, "dx of all stages must fit in the stage block storage");
     for (int t = tid; t < NX; t += nt) { dxall[t] = 0.0; w.DX[t] = 0.0; }
@@ -1440,14 +1437,6 @@ struct Solver {
 
   // ---- trial point (x + a dx, u + a du, s + a ds) for the line search: constraint violation theta, cost (with and
   // without the regularisation term), sum ln s, max unrelaxed violation.  CTA-wide like the eval pass.
-#ifdef CMPC_TRIAL_SERIAL
-  CMPC_HD void trial(double alpha, double* out) {
-    const int N = c.N;
-    for (int i = par.tid(); i <= N; i += par.nt()) stage_trial(c, in, w, i, sm.mask[i], alpha, sm.acc[i]);
-    par.sync();
-    reduce_trial(out);
-  }
-#else
   CMPC_HD void trial(double alpha, double* out) {
     const int N = c.N, tid = par.tid(), nt = par.nt();
     TrialScratch* ts = reinterpret_cast<TrialScratch*>(sm.M);
@@ -1612,7 +1601,6 @@ struct Solver {
     }
     reduce_trial(out);
   }
-#endif
 
   CMPC_HD void reduce_trial(double* out) {
     const int N = c.N;

@@ -49,7 +49,10 @@ int hostsim_stage_debug(int N, const double* x0, const double* com_ref, const do
   double acc[8];
   stage_derivs(c, in, w, i, sm->mask[i], mu, acc);
   for (int j = 0; j < 60; ++j) grad_out[j] = cmpc_dbg_rd[j];
-  sol.assemble_stage(i, 0.0);
+  for (int t = 0; t < NX * NX; ++t) sm->P[t] = 0.0;
+  for (int t = 0; t < NX; ++t) sm->pv[t] = 0.0;
+  for (int t = 0; t < Q_RG; ++t) sm->recb[0][t] = w.REC[(size_t)i * RECSZ + t];
+  sol.assemble_stage(i, 0.0, sm->recb[0]);
   for (int r = 0; r < 60; ++r) for (int cc = 0; cc < 60; ++cc) {
     const int a = r < NU ? r : r + NW, b = cc < NU ? cc : cc + NW;
     M_out[r * 60 + cc] = sm->M[mi(a >= b ? a : b, a >= b ? b : a)];
