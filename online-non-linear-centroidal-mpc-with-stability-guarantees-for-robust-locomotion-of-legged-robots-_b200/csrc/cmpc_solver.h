@@ -35,6 +35,7 @@ constexpr int F_K = 0, F_P = F_K + KSZ, F_PV = F_P + NX * NX;   // K | k, cost-t
 constexpr int FACSZ = F_PV + NX;            // 1798 doubles
 constexpr int FWDBUF = KSZ + NX;            // forward sweep staging of one stage: K | k | d
 constexpr int NTILE = 15 * 16 / 2;          // 4 x 4 tiles of the padded 64 x 64 lower triangle right of tile column 0 (120)
+constexpr int NLY = 33 + 3 * 66;               // entries of the stage block the Lyapunov row touches: 33 gradient + 198 same-axis pairs
 constexpr int PSTR = 17;                    // doubles between tile rows of the pivot panel (odd: lanes with different tile rows hit different banks)
 // per-stage derivative record written by the eval pass
 constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
@@ -116,6 +117,8 @@ struct Smem {
   short csr_ptr[NX + 1];      // structural pattern of [B A] by rows (gather form)
   unsigned char csr_idx[NZ * 4];
   signed char barow[NZ * 4];  // ba_row(j, q) table
+  unsigned short ly_m[NLY], ly_s[NLY];   // Lyapunov row scatter table: index into M, index of the coefficient in the record
+  unsigned char ly_g[NLY];               // ... and the two gamma selectors (0: left, 1: right, 2: none), 4 bits each
 };
 
 struct Stats { double cost, viol, kkt, mu; int iters, status, nfact, nreg; };
@@ -854,13 +857,14 @@ struct Solver {
     const double* bav = R + Q_BA;
     for (int t = tid; t < MSZ; t += nt) sm.M[t] = 0.0;
     // W = P [B A]  (28 x 60): warp per row r, lanes over columns j;  tv = p + P d
-    for (int r = wid; r < NX; r += nw) {
-      const double* Pr = sm.P + r * NX;
-      for (int j = lane; j < NZ; j += nl) {
-        double s = 0.0;
+    // (a lane keeps the row pattern and the values of its column over the rows it visits; empty slots read P(r, 0) times 0)
+    for (int j = lane; j < NZ; j += nl) {
+      int rr[4]; double bv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int rr = sm.barow[4 * j + q]; if (rr >= 0) s += Pr[rr] * bav[4 * j + q]; }
-        sm.W[r * NZ + j] = s;
+      for (int q = 0; q < 4; ++q) { const int r0 = sm.barow[4 * j + q]; bv[q] = r0 >= 0 ? bav[4 * j + q] : 0.0; rr[q] = r0 >= 0 ? r0 : 0; }
+      for (int r = wid; r < NX; r += nw) {
+        const double* Pr = sm.P + r * NX;
+        sm.W[r * NZ + j] = (Pr[rr[0]] * bv[0] + Pr[rr[1]] * bv[1]) + (Pr[rr[2]] * bv[2] + Pr[rr[3]] * bv[3]);
       }
     }
     for (int r = tid; r < NX; r += nt) {
@@ -899,25 +903,15 @@ struct Solver {
       }
     }
     par.sync();
-    // Lyapunov row: lam * C (x) I_3 curvature over the 33 touched variables (same-axis pairs), and its gradient as
-    // row/column NU.  Touched variable a (0..32): forces 0..23 (type F, scaled by gamma_e), then p, v, theta.
-    for (int ai = wid; ai < 33; ai += nw) {
-      int ma, ta, xa; double sa;
-      if (ai < 24) { ma = ai; ta = 3; xa = ai % 3; sa = R[Q_GAM + ai / 12]; }
-      else { const int q = ai - 24; ta = q / 3; xa = q % 3; sa = 1.0; ma = XO + (ta == 0 ? IP : (ta == 1 ? IV : ITH)) + xa; }
-      if (lane == 0) {
-        const double gv = sa * R[Q_LG + 3 * ta + xa];
-        if (ma < NU) sm.M[mi(NU, ma)] = gv; else sm.M[mi(ma, NU)] = gv;
-      }
-      if (sa == 0.0) continue;
-      // same-axis partners only: bi = xa, xa + 3, ... (forces and states keep the axis in the low index)
-      for (int bq = lane; 3 * bq + xa <= ai; bq += nl) {
-        const int bi = 3 * bq + xa;
-        int mb, tb; double sb;
-        if (bi < 24) { mb = bi; tb = 3; sb = R[Q_GAM + bi / 12]; }
-        else { const int q = bi - 24; tb = q / 3; sb = 1.0; mb = XO + (tb == 0 ? IP : (tb == 1 ? IV : ITH)) + xa; }
-        const double v = sa * sb * R[Q_LC + 4 * ta + tb];
-        if (ma >= mb) sm.M[mi(ma, mb)] += v; else sm.M[mi(mb, ma)] += v;
+    // Lyapunov row: its gradient as row / column NU and the curvature lam * C (x) I_3 over the same-axis pairs of the 33
+    // touched variables, scattered through the table built once per solve
+    {
+      const double gam3[3] = {R[Q_GAM], R[Q_GAM + 1], 1.0};
+      for (int e = tid; e < NLY; e += nt) {
+        const int g = sm.ly_g[e];
+        const int ga = g & 15, gb = g >> 4;
+        const double va = ga == 0 ? gam3[0] : (ga == 1 ? gam3[1] : 1.0), vb = gb == 0 ? gam3[0] : (gb == 1 ? gam3[1] : 1.0);
+        sm.M[sm.ly_m[e]] += va * vb * R[sm.ly_s[e]];
       }
     }
     // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u); cross-axis pairs only, so
@@ -1005,14 +999,12 @@ struct Solver {
       for (int a_ = wid; a_ <= NZ; a_ += nw) {
         if (a_ < NZ) {
           int rr[4]; double bv[4];
+          if (sm.barow[4 * a_] < 0) continue;                    // structurally empty column (previous-f_z states)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { rr[q] = sm.barow[4 * a_ + q]; bv[q] = bav[4 * a_ + q]; }
-          if (rr[0] < 0) continue;                               // structurally empty column (previous-f_z states)
+          for (int q = 0; q < 4; ++q) { const int r0 = sm.barow[4 * a_ + q]; bv[q] = r0 >= 0 ? bav[4 * a_ + q] : 0.0; rr[q] = (r0 >= 0 ? r0 : 0) * NZ; }
           double* Mr = sm.M + mi(mz(a_), 0);
           for (int b_ = lane; b_ <= a_; b_ += nl) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (rr[q] >= 0) s += bv[q] * sm.W[rr[q] * NZ + b_];
+            const double s = (bv[0] * sm.W[rr[0] + b_] + bv[1] * sm.W[rr[1] + b_]) + (bv[2] * sm.W[rr[2] + b_] + bv[3] * sm.W[rr[3] + b_]);
             Mr[mz(b_)] += s;
           }
         } else {
@@ -1633,7 +1625,8 @@ struct Solver {
   // ---- solve with retries.  An interior-point method started next to the boundary of a changed active set can jam,
   // and the non-convex end game occasionally stalls a few 1e-8 short of the tolerance: a failed warm solve is repeated
   // from the solver's own cold start, a failed cold solve again with a ten times larger, then a ten times smaller initial barrier (other central paths).
-  CMPC_HD void run(int warm, Stats* st) {
+  // ---- per-solve tables: structural pattern of [B A], Lyapunov constants and scatter table, tile map
+  CMPC_HD void setup() {
     if (par.tid() == 0) {                                  // structural pattern of [B A]: by column (ba_row) and by row (gather)
       int n = 0;
       for (int t = 0; t < NZ * 4; ++t) sm.barow[t] = (signed char)ba_row(t >> 2, t & 3);
@@ -1644,6 +1637,33 @@ struct Solver {
       sm.csr_ptr[NX] = (short)n;
     }
     if (par.tid() == 0) lyapunov_consts(c, in, sm.lyapC);
+    // Lyapunov row: which entries of the stage block it touches, with which coefficient.  Touched variable a (0..32):
+    // forces 0..23 (type F, scaled by gamma_e), then p, v, theta; curvature lam * C (x) I_3 couples same-axis pairs only.
+    for (int e = par.tid(); e < NLY; e += par.nt()) {
+      int ai, bi = -1;
+      if (e < 33) ai = e;
+      else {                                     // pair index within the axis: 66 pairs (bq <= aq) of 11 same-axis variables
+        const int q = e - 33, xa = q / 66, pq = q % 66;
+        int aq = 0; while ((aq + 1) * (aq + 2) / 2 <= pq) ++aq;
+        const int bq = pq - aq * (aq + 1) / 2;
+        ai = 3 * aq + xa; bi = 3 * bq + xa;
+      }
+      auto var = [](int a, int& mm, int& tt, int& gg) {
+        if (a < 24) { mm = a; tt = 3; gg = a / 12; }
+        else { const int q = a - 24; tt = q / 3; gg = 2; mm = XO + (tt == 0 ? IP : (tt == 1 ? IV : ITH)) + q % 3; }
+      };
+      int ma, ta, ga; var(ai, ma, ta, ga);
+      if (bi < 0) {
+        sm.ly_m[e] = (unsigned short)(ma < NU ? mi(NU, ma) : mi(ma, NU));
+        sm.ly_s[e] = (unsigned short)(Q_LG + 3 * ta + ai % 3);
+        sm.ly_g[e] = (unsigned char)(ga | (2 << 4));
+      } else {
+        int mb, tb, gb; var(bi, mb, tb, gb);
+        sm.ly_m[e] = (unsigned short)(ma >= mb ? mi(ma, mb) : mi(mb, ma));
+        sm.ly_s[e] = (unsigned short)(Q_LC + 4 * ta + tb);
+        sm.ly_g[e] = (unsigned char)(ga | (gb << 4));
+      }
+    }
     for (int sl = 0; sl < Par::TPT; ++sl) {
       const int tile = par.tid() + sl * par.nt();                   // tile (ti, tj), ti >= tj >= 1, row-major in the triangle
       int ti = 0;
@@ -1652,6 +1672,10 @@ struct Solver {
       tile_j[sl] = tile < NTILE ? tile - ti * (ti + 1) / 2 + 1 : 0;
     }
     par.sync();
+  }
+
+  CMPC_HD void run(int warm, Stats* st) {
+    setup();
     // attempts: as asked (warm or cold, mu_init) -> cold, mu_init -> cold, 10 mu_init -> cold, mu_init / 10
     mu_scale = 1.0;
     run_once(warm, st);

@@ -45,6 +45,7 @@ int hostsim_stage_debug(int N, const double* x0, const double* com_ref, const do
   ParSerial par;
   Solver<ParSerial> sol(c, in, w, *sm, par);
   double pv; build_masks(c, in, sm->mask, &pv);
+  sol.setup();
   sol.mu = mu;
   double acc[8];
   stage_derivs(c, in, w, i, sm->mask[i], mu, acc);
@@ -72,7 +73,7 @@ int hostsim_eval_compare(int N, const double* x0, const double* com_ref, const d
   ParSerial par;
   Solver<ParSerial> sol(c, in, w, *sm, par);
   double pv; build_masks(c, in, sm->mask, &pv);
-  lyapunov_consts(c, in, sm->lyapC);
+  sol.setup();
   double ev[8];
   sol.eval(ev);
   std::vector<double> rec_new(w.REC, w.REC + (size_t)(N + 1) * RECSZ);
