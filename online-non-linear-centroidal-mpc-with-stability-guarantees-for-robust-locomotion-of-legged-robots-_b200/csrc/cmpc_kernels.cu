@@ -33,7 +33,11 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 #define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(-2, what, e_); } while (0)
 
+extern __shared__ __align__(16) unsigned char cmpc_smem_raw[];     // the CTA's dynamic shared memory (one Smem)
+
 struct ParCta {
+  template <class T> __device__ T& smem() const { return *reinterpret_cast<T*>(cmpc_smem_raw); }
+  __device__ void bind(void*) const {}
   __device__ int tid() const { return (int)threadIdx.x; }
   __device__ int nt() const { return (int)blockDim.x; }
   __device__ void sync() const { __syncthreads(); }
@@ -67,8 +71,7 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
                   const double* __restrict__ foot_ref, const double* __restrict__ gamma,
                   const double* __restrict__ mass, const double* __restrict__ k1, double* work, size_t wstride,
                   int warm, Outputs out, const int32_t* __restrict__ perm, int32_t* __restrict__ last_iters) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  Smem& sm = *reinterpret_cast<Smem*>(cmpc_smem_raw);
   const int N = c.N;
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0) for (int k = 0; k < PF_COUNT; ++k) sm.prof[k] = 0;

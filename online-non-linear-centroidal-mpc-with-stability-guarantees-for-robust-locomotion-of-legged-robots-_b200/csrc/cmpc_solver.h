@@ -59,6 +59,16 @@ static int cmpc_trace_on = 0;
 static double cmpc_dbg_rd[64];
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define CMPC_SCHED_FENCE() asm volatile("" ::: "memory")
+// the workspace and the instance data are global memory (lets the compiler emit LDG / STG instead of generic accesses)
+#define CMPC_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define CMPC_SCHED_FENCE() do {} while (0)
+#define CMPC_ASSUME_GLOBAL(p) do {} while (0)
+#endif
+
+
 CMPC_HD double cmpc_rcp(double x) {
 #if defined(__CUDA_ARCH__)
   return __drcp_rn(x);
@@ -98,7 +108,7 @@ CMPC_HD Work carve_work(double* base, int N) {
 }
 
 // Shared-memory block of one instance.
-struct Smem {
+struct alignas(16) Smem {
   double M[MSZ];             // stage KKT block [u ; w ; x] (+ gradient row 62), packed lower triangle
   double W[NX * NZ];         // P * [B A]
   double P[NX * NX];         // cost-to-go Hessian of stage i+1 (full symmetric)
@@ -382,78 +392,102 @@ static_assert(TCH >= 8, "trial scratch does not fit");
 // ---------------------------------------------------------------------------------------------
 template <class Par>
 struct Solver {
-  const Config& c; const Instance& in; Work w; Smem& sm; Par& par;
+  // (the shared-memory block is not a member: every member function takes it from the execution policy, which on the
+  // GPU derives it from the CTA's dynamic shared-memory symbol -- the compiler then knows the address space and emits
+  // LDS / STS instead of generic loads and stores)
+  const Config& c; const Instance& in; Work w; Par& par;
   double mu, reg_last, mu_scale;
   int nfact, nreg;
   int tile_i[Par::TPT], tile_j[Par::TPT];     // this thread's 4 x 4 register tiles of the stage block (row, column; -1 = none)
 
   CMPC_HD Solver(const Config& c_, const Instance& in_, const Work& w_, Smem& sm_, Par& par_)
-      : c(c_), in(in_), w(w_), sm(sm_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0) {}
+      : c(c_), in(in_), w(w_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0) { par.bind(&sm_); }
+
+  // workspace sections, known to be global memory
+  CMPC_HD double* gX() const { double* p = w.X; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gU() const { double* p = w.U; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gY() const { double* p = w.Y; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gS() const { double* p = w.S; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gLAM() const { double* p = w.LAM; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDX() const { double* p = w.DX; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDU() const { double* p = w.DU; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDS() const { double* p = w.DS; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gYN() const { double* p = w.YN; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDW() const { double* p = w.DW; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gREC() const { double* p = w.REC; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gFAC() const { double* p = w.FAC; CMPC_ASSUME_GLOBAL(p); return p; }
+
+  // instance data, global memory as well
+  CMPC_HD const double* i_x0() const { const double* p = in.x0; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_com_ref() const { const double* p = in.com_ref; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_foot_ref() const { const double* p = in.foot_ref; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_gamma() const { const double* p = in.gamma; CMPC_ASSUME_GLOBAL(p); return p; }
 
   CMPC_HD static int tri(int r, int cidx) { return r * (r + 1) / 2 + cidx; }
 
   // ---- initial point.  warm: 0 = cold (solver's own guess), 1 = primal (X, U given; slacks/duals reset as
   // IPOPT does), 2 = full (X, U, Y, S, LAM given).
   CMPC_HD void init_point(int warm) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
     if (warm == 0) {
       for (int t = tid; t < (N + 1) * NX; t += nt) {
         const int i = t / NX, j = t % NX;
-        w.X[t] = (j < NXP) ? in.x0[j] : 0.0;
+        gX()[t] = (j < NXP) ? i_x0()[j] : 0.0;
         (void)i;
       }
       for (int t = tid; t < N * NU; t += nt) {
         const int i = t / NU, j = t % NU;
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         double v = 0.0;
         if (j < 24 && j % 3 == 2) {
           const double ge = (j < 12) ? gl : gr;
           v = ge * in.mass * c.grav / (4.0 * (gl + gr > 0.5 ? gl + gr : 1.0));
         }
-        w.U[t] = v;
+        gU()[t] = v;
       }
       par.sync();
       for (int t = tid; t < (N + 1) * NQ; t += nt) {
         const int i = t / NQ, v = t % NQ;
-        w.X[i * NX + IQ + v] = (i >= 1) ? w.U[(i - 1) * NU + 3 * v + 2] : 0.0;
+        gX()[i * NX + IQ + v] = (i >= 1) ? gU()[(i - 1) * NU + 3 * v + 2] : 0.0;
       }
     }
     if (warm == 3) {
       // MPC shift: the previous tick's stage i+1 becomes this tick's stage i (the last stage is repeated).  Staged
       // through the step buffers so the in-place move is race free.
-      for (int t = tid; t < N * NX; t += nt) { w.DX[t] = w.X[t + NX]; w.YN[t] = w.Y[t + NX]; }
-      for (int t = tid; t < (N - 1) * NU; t += nt) w.DU[t] = w.U[t + NU];
+      for (int t = tid; t < N * NX; t += nt) { gDX()[t] = gX()[t + NX]; gYN()[t] = gY()[t + NX]; }
+      for (int t = tid; t < (N - 1) * NU; t += nt) gDU()[t] = gU()[t + NU];
       for (int t = tid; t < (N - 1) * NR; t += nt) {
         const int r = t % NR;
         // rows that exist only at stage 0 (angular momentum) keep their own history
-        w.DS[t] = (r == R_HW && t < NR) ? w.S[t] : w.S[t + NR];
+        gDS()[t] = (r == R_HW && t < NR) ? gS()[t] : gS()[t + NR];
       }
       par.sync();
-      for (int t = tid; t < N * NX; t += nt) { w.X[t] = w.DX[t]; w.Y[t] = w.YN[t]; }
-      for (int t = tid; t < (N - 1) * NU; t += nt) w.U[t] = w.DU[t];
-      for (int t = tid; t < (N - 1) * NR; t += nt) w.S[t] = w.DS[t];
+      for (int t = tid; t < N * NX; t += nt) { gX()[t] = gDX()[t]; gY()[t] = gYN()[t]; }
+      for (int t = tid; t < (N - 1) * NU; t += nt) gU()[t] = gDU()[t];
+      for (int t = tid; t < (N - 1) * NR; t += nt) gS()[t] = gDS()[t];
       par.sync();
-      for (int t = tid; t < (N - 1) * NR; t += nt) { const int r = t % NR; w.DS[t] = (r == R_HW && t < NR) ? w.LAM[t] : w.LAM[t + NR]; }
+      for (int t = tid; t < (N - 1) * NR; t += nt) { const int r = t % NR; gDS()[t] = (r == R_HW && t < NR) ? gLAM()[t] : gLAM()[t + NR]; }
       par.sync();
-      for (int t = tid; t < (N - 1) * NR; t += nt) w.LAM[t] = w.DS[t];
+      for (int t = tid; t < (N - 1) * NR; t += nt) gLAM()[t] = gDS()[t];
       par.sync();
       warm = 2;
     }
-    for (int t = tid; t < NX; t += nt) w.X[t] = (t < NXP) ? in.x0[t] : 0.0;      // x_0 is data
-    if (warm < 2) for (int t = tid; t < (N + 1) * NX; t += nt) w.Y[t] = 0.0;
+    for (int t = tid; t < NX; t += nt) gX()[t] = (t < NXP) ? i_x0()[t] : 0.0;      // x_0 is data
+    if (warm < 2) for (int t = tid; t < (N + 1) * NX; t += nt) gY()[t] = 0.0;
     par.sync();
     if (warm < 2) {
       mu = c.mu_init * mu_scale;
       for (int i = tid; i <= N; i += nt) {
         double x[NX], u[NU], xp[NX], g[NR];
-        for (int j = 0; j < NX; ++j) x[j] = w.X[i * NX + j];
-        if (i < N) { for (int j = 0; j < NU; ++j) u[j] = w.U[i * NU + j]; dyn_step(c, in, i, x, u, xp); }
+        for (int j = 0; j < NX; ++j) x[j] = gX()[i * NX + j];
+        if (i < N) { for (int j = 0; j < NU; ++j) u[j] = gU()[i * NU + j]; dyn_step(c, in, i, x, u, xp); }
         else { for (int j = 0; j < NU; ++j) u[j] = 0.0; for (int j = 0; j < NX; ++j) xp[j] = x[j]; }
         stage_ineq(c, in, i, sm.mask[i], x, u, xp, g);
         for (int r = 0; r < NR; ++r) {
           double sv = 1.0, lv = 0.0;
           if (sm.mask[i] & (1ull << r)) { sv = -(g[r] - c.relax); sv = sv > c.bound_push ? sv : c.bound_push; lv = 1.0; }
-          w.S[i * NR + r] = sv; w.LAM[i * NR + r] = lv;
+          gS()[i * NR + r] = sv; gLAM()[i * NR + r] = lv;
         }
       }
     } else {
@@ -461,12 +495,12 @@ struct Solver {
       // keep the previous slacks/multipliers but push them off the boundary: s >= sqrt(mu)*1e-2, lam = mu/s floor
       for (int t = tid; t < (N + 1) * NR; t += nt) {
         const int i = t / NR, r = t % NR;
-        if (!(sm.mask[i] & (1ull << r))) { w.S[t] = 1.0; w.LAM[t] = 0.0; continue; }
-        double sv = w.S[t], lv = w.LAM[t];
+        if (!(sm.mask[i] & (1ull << r))) { gS()[t] = 1.0; gLAM()[t] = 0.0; continue; }
+        double sv = gS()[t], lv = gLAM()[t];
         if (!(sv > c.warm_push)) sv = c.warm_push;
         if (!(lv > mu / sv * 1e-3)) lv = mu / sv * 1e-3;
         if (c.warm_comp > 0.0 && lv > mu / sv * c.warm_comp) lv = mu / sv * c.warm_comp;
-        w.S[t] = sv; w.LAM[t] = lv;
+        gS()[t] = sv; gLAM()[t] = lv;
       }
     }
     par.sync();
@@ -483,6 +517,7 @@ struct Solver {
   CMPC_HD static void stat_dual(double* st, double r) { const double ar = fabs(r); st[1] = ar > st[1] ? ar : st[1]; }
 
   CMPC_HD void eval(double* out) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
     EvalScratch* es = reinterpret_cast<EvalScratch*>(sm.M);
     const double d = c.delta, m = in.mass, k1 = in.k1;
@@ -491,7 +526,7 @@ struct Solver {
       // ---- P0: yaw sines / cosines; role statistics cleared
       for (int t = tid; t < ns * 2; t += nt) {
         const int il = t >> 1, e = t & 1, i = i0 + il;
-        const double psi = w.X[i * NX + (e ? IPSR : IPSL)];
+        const double psi = gX()[i * NX + (e ? IPSR : IPSL)];
         es[il].cs[e] = cos(psi); es[il].sn[e] = sin(psi);
       }
       for (int t = tid; t < ns * 11; t += nt) {
@@ -504,7 +539,7 @@ struct Solver {
         const int il = t >> 3, v = t & 7, i = i0 + il;
         if (i >= N) continue;
         const int e = v >> 2, k = v & 3;
-        const double* x = w.X + i * NX; const double* u = w.U + i * NU; const double* yn = w.Y + (i + 1) * NX;
+        const double* x = gX() + i * NX; const double* u = gU() + i * NU; const double* yn = gY() + (i + 1) * NX;
         const double* pe = x + (e ? IPR : IPL);
         const double cs = es[il].cs[e], sn = es[il].sn[e];
         double cx, cy; corner(c, k, cx, cy);
@@ -523,7 +558,7 @@ struct Solver {
       for (int t = tid; t < ns * 17; t += nt) {
         const int il = t / 17, q = t - il * 17, i = i0 + il;
         if (i >= N) continue;
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         const double (*pt)[10] = es[il].part;
         double s = 0.0;
         if (q < 6) { const int e = q / 3, j = q - 3 * e; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][j]; }
@@ -538,11 +573,11 @@ struct Solver {
         const int i = i0 + il;
         if (i >= N) continue;
         EvalScratch& E = es[il];
-        const double* x = w.X + i * NX; const double* yn = w.Y + (i + 1) * NX;
-        const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR;
-        double* rec = w.REC + (size_t)i * RECSZ;
+        const double* x = gX() + i * NX; const double* yn = gY() + (i + 1) * NX;
+        const double* s = gS() + i * NR; const double* lam = gLAM() + i * NR;
+        double* rec = gREC() + (size_t)i * RECSZ;
         const uint64_t mask = sm.mask[i];
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         for (int j = 0; j < 3; ++j) { E.F[j] = gl * E.sum[j] + gr * E.sum[3 + j]; E.xph[j] = x[IH + j] + d * E.sum[6 + j]; }
         const double q = lyapunov_grad(c, in, i, x, E.F, E.LG);
         double* st = E.st[10];
@@ -567,7 +602,7 @@ struct Solver {
         for (int j = 0; j < 3; ++j) { rec[Q_HP + j] = E.xph[j]; rec[Q_YH + j] = d * yn[IH + j]; }
         for (int e = 0; e < 2; ++e) {
           rec[Q_GAM + e] = e ? gr : gl;
-          rec[Q_GAMP + e] = (i >= 1) ? in.gamma[2 * (i - 1) + e] * c.w_rate : 0.0;
+          rec[Q_GAMP + e] = (i >= 1) ? i_gamma()[2 * (i - 1) + e] * c.w_rate : 0.0;
         }
       }
       par.sync();
@@ -576,14 +611,14 @@ struct Solver {
         const int role = t / ns, il = t - role * ns, i = i0 + il;
         const bool has_u = i < N;
         EvalScratch& E = es[il];
-        const double* x = w.X + i * NX; const double* yi = w.Y + i * NX;
-        const double* u = w.U + (has_u ? i : 0) * NU;                 // (not read at the terminal stage)
-        const double* yn = w.Y + (has_u ? i + 1 : i) * NX;
-        const double* xn = w.X + (has_u ? i + 1 : i) * NX;
-        const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR;
-        double* rec = w.REC + (size_t)i * RECSZ;
+        const double* x = gX() + i * NX; const double* yi = gY() + i * NX;
+        const double* u = gU() + (has_u ? i : 0) * NU;                 // (not read at the terminal stage)
+        const double* yn = gY() + (has_u ? i + 1 : i) * NX;
+        const double* xn = gX() + (has_u ? i + 1 : i) * NX;
+        const double* s = gS() + i * NR; const double* lam = gLAM() + i * NR;
+        double* rec = gREC() + (size_t)i * RECSZ;
         const uint64_t mask = sm.mask[i];
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         double* st = E.st[role];
         const double lamL = has_u ? E.sc[2] : 0.0, lamH = has_u ? E.sc[5] : 0.0;
         const bool x_free = i >= 1;                                   // x_0 is data: its dual residual is not a residual
@@ -604,7 +639,7 @@ struct Solver {
           const double rr[3] = {rx + pe[0] - x[0], ry + pe[1] - x[1], pe[2] - x[2]};
           rec[Q_DR + 2 * v] = -sn * cx - cs * cy; rec[Q_DR + 2 * v + 1] = cs * cx - sn * cy;
           const double fv[3] = {u[3 * v], u[3 * v + 1], u[3 * v + 2]};
-          const double gp = (i >= 1) ? in.gamma[2 * (i - 1) + e] * c.w_rate : 0.0;
+          const double gp = (i >= 1) ? i_gamma()[2 * (i - 1) + e] * c.w_rate : 0.0;
           const double dz = fv[2] - x[IQ + v];
           double a_gc[3], a_dg[3], a_m1[3] = {0, 0, 0}, a_m2[3] = {0, 0, 0}, a_gl[3] = {0, 0, 0};
           for (int j = 0; j < 3; ++j) {
@@ -670,8 +705,8 @@ struct Solver {
           }
         } else if (role == 8) {
           // ---------------- CoM role: p, v, h, theta
-          const double* refp = in.com_ref + 9 * (i >= 1 ? i - 1 : 0);         // tracking reference column i-1
-          const double* ref = in.com_ref + 9 * (has_u ? i : 0);               // dynamics / Lyapunov reference column i
+          const double* refp = i_com_ref() + 9 * (i >= 1 ? i - 1 : 0);         // tracking reference column i-1
+          const double* ref = i_com_ref() + 9 * (has_u ? i : 0);               // dynamics / Lyapunov reference column i
           const double wz = (i >= 1) ? wz_of(c, i - 1) : 0.0;
 #pragma unroll
           for (int cidx = 0; cidx < 12; ++cidx) {
@@ -722,7 +757,7 @@ struct Solver {
           }
         } else {
           // ---------------- feet role: yaw / position states of both feet, foot velocity / yaw-rate inputs
-          const double* fr = in.foot_ref + 8 * (i >= 1 ? i - 1 : 0);
+          const double* fr = i_foot_ref() + 8 * (i >= 1 ? i - 1 : 0);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const double ge = e ? gr : gl;
@@ -808,6 +843,7 @@ struct Solver {
 
   // tiny reduction over <= 65 stages done redundantly by every thread (broadcast reads)
   CMPC_HD void reduce_acc(double* out) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N;
     double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0;
     for (int i = 0; i <= N; ++i) {
@@ -821,6 +857,7 @@ struct Solver {
   }
 
   CMPC_HD int n_rows_total() const {
+    Smem& sm = par.template smem<Smem>();
     int n = 0;
     for (int i = 0; i <= c.N; ++i) { uint64_t m = sm.mask[i]; while (m) { n += (int)(m & 1ull); m >>= 1; } }
     return n;
@@ -852,6 +889,7 @@ struct Solver {
   // disjoint sets of entries.  The products W = P [B A] and tv = p + P d of the cost-to-go term are formed alongside
   // the first phase (they do not touch M).
   CMPC_HD void assemble_stage(int i, double reg, const double* R) {
+    Smem& sm = par.template smem<Smem>();
     const int tid = par.tid(), nt = par.nt();
     const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
     const double* bav = R + Q_BA;
@@ -961,7 +999,7 @@ struct Solver {
 
   // asynchronous copy of stage i's derivative record (without the row residuals) into a staging buffer
   CMPC_HD void record_in(int i, double* buf) {
-    par.copy_async(buf, w.REC + (size_t)i * RECSZ, Q_RG);
+    par.copy_async(buf, gREC() + (size_t)i * RECSZ, Q_RG);
     par.commit_async();
   }
 
@@ -971,11 +1009,12 @@ struct Solver {
   // -- the stage block is sparse: stance-foot inputs, swing-foot forces, previous-f_z states -- are skipped
   // without divergence.
   CMPC_HD bool backward(double reg) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
     const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
     par.wait_async();                                              // (a sweep abandoned on a bad pivot may have left a record copy in flight)
     {   // terminal stage: P_N diagonal, p_N = modified gradient (x part)
-      const double* rec = w.REC + (size_t)N * RECSZ;
+      const double* rec = gREC() + (size_t)N * RECSZ;
       for (int t = tid; t < NX * NX; t += nt) sm.P[t] = 0.0;
       par.sync();
       for (int t = tid; t < NX; t += nt) {
@@ -986,7 +1025,7 @@ struct Solver {
     }
     record_in(N - 1, sm.recb[(N - 1) & 1]);
     for (int i = N - 1; i >= 0; --i) {
-      double* fac = w.FAC + (size_t)i * FACSZ;
+      double* fac = gFAC() + (size_t)i * FACSZ;
       CMPC_TIC(sm);
       par.wait_async();
       par.sync();                                                  // record i is in; every thread is done with stage i + 1
@@ -1248,8 +1287,13 @@ struct Solver {
         for (int k = NA - 1; k >= 0; --k) {
           const double zk = v[k] * sm.rdiag[k];
           v[k] = zk;
+          // (chunks of eight with a scheduling fence: the row of L must not be loaded whole ahead of time, v[] needs the registers)
 #pragma unroll
-          for (int j = 0; j < k; ++j) v[j] -= sm.M[mi(k, j)] * zk;
+          for (int j0 = 0; j0 < k; j0 += 8) {
+#pragma unroll
+            for (int j = j0; j < j0 + 8 && j < k; ++j) v[j] -= sm.M[mi(k, j)] * zk;
+            CMPC_SCHED_FENCE();
+          }
         }
 #pragma unroll
         for (int q = 0; q < NA; ++q) sm.W[t * NA + q] = v[q];          // W (28 x 60) is free here: K staged as 29 x 34
@@ -1273,8 +1317,8 @@ struct Solver {
   // barriers per stage, the next stage's K | k | d | [B A] values arrive by asynchronous copy while the current stage
   // is computed), then the full-step costates y_i = p_i + P_i dx_i of all stages at once.
   CMPC_HD void stage_in(int i, double* kb, double* bb) {
-    const double* fac = w.FAC + (size_t)i * FACSZ;
-    const double* rec = w.REC + (size_t)i * RECSZ;
+    const double* fac = gFAC() + (size_t)i * FACSZ;
+    const double* rec = gREC() + (size_t)i * RECSZ;
     par.copy_async(kb, fac + F_K, KSZ);
     par.copy_async(kb + KSZ, rec + Q_D, NX);
     par.copy_async(bb, rec + Q_BA, NZ * 4);
@@ -1282,13 +1326,14 @@ struct Solver {
   }
 
   CMPC_HD void forward(double reg) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
     double* dxall = sm.M;                                        // dx of all stages, (N + 1) x NX: the stage block is idle here
     double* kbuf[2] = {sm.W, sm.W + FWDBUF};                     // W | P storage (contiguous, idle here)
     double* bbuf[2] = {sm.recb[0], sm.W + 2 * FWDBUF};
     static_assert(2 * FWDBUF + NZ * 4 <= NX * NZ + NX * NX, "forward staging must fit in W | P");
     static_assert((NMAX + 1) * NX <= MSZ, "dx of all stages must fit in the stage block storage");
-    for (int t = tid; t < NX; t += nt) { dxall[t] = 0.0; w.DX[t] = 0.0; }
+    for (int t = tid; t < NX; t += nt) { dxall[t] = 0.0; gDX()[t] = 0.0; }
     stage_in(0, kbuf[0], bbuf[0]);
     par.wait_async();
     par.sync();
@@ -1304,7 +1349,7 @@ struct Solver {
         for (int r = 0; r < NX; r += 2) { s0 += K[r * NA + cidx] * dx[r]; s1 += K[(r + 1) * NA + cidx] * dx[r + 1]; }
         const double s = s0 + s1;
         sm.zs[cidx] = s;
-        if (cidx < NU) w.DU[i * NU + cidx] = s; else w.DW[i * NW + cidx - NU] = s;
+        if (cidx < NU) gDU()[i * NU + cidx] = s; else gDW()[i * NW + cidx - NU] = s;
       }
       par.sync();
       // dx_{i+1} = d + A dx + B du   (row gather over the structural pattern)
@@ -1315,7 +1360,7 @@ struct Solver {
           s += bav[jq] * (j < NU ? sm.zs[j] : dx[j - NU]);
         }
         dxall[(i + 1) * NX + r] = s;
-        w.DX[(i + 1) * NX + r] = s;
+        gDX()[(i + 1) * NX + r] = s;
       }
       par.wait_async();
       par.sync();
@@ -1326,16 +1371,16 @@ struct Solver {
       const double* dx = dxall + i * NX;
       double s;
       if (i < N) {
-        const double* fac = w.FAC + (size_t)i * FACSZ;
+        const double* fac = gFAC() + (size_t)i * FACSZ;
         double s0 = fac[F_PV + r], s1 = 0.0;
 #pragma unroll
         for (int j = 0; j < NX; j += 2) { s0 += fac[F_P + j * NX + r] * dx[j]; s1 += fac[F_P + (j + 1) * NX + r] * dx[j + 1]; }
         s = s0 + s1;
       } else {
-        const double* rec = w.REC + (size_t)N * RECSZ;
+        const double* rec = gREC() + (size_t)N * RECSZ;
         s = rec[Q_GC + 32 + r] + mu * rec[Q_M1 + 32 + r] + rec[Q_M2 + 32 + r] + (rec[Q_DIAG + 32 + r] + reg) * dx[r];
       }
-      w.YN[t] = s;
+      gYN()[t] = s;
     }
     par.sync();
   }
@@ -1344,6 +1389,7 @@ struct Solver {
   // steps, the fraction-to-boundary step lengths and the directional derivative of the barrier function.
   // CTA-wide: items are (stage, role) with the roles of the eval pass (8 vertices, CoM rows, foot rows).
   CMPC_HD void slack_steps(double tau, double* a_p, double* a_d, double* dphi) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
     double (*st)[4] = reinterpret_cast<double (*)[4]>(sm.M);       // [(N + 1) * 10][4]: a_p, a_d, grad'dz, sum ds/s per item
     static_assert((NMAX + 1) * 10 * 4 <= MSZ + NX * NZ, "slack step scratch must fit in M | W");
@@ -1351,9 +1397,9 @@ struct Solver {
       const int role = t / (N + 1), i = t - role * (N + 1);
       const bool has_u = i < N;
       const uint64_t mask = sm.mask[i];
-      const double* dx = w.DX + i * NX; const double* du = w.DU + (has_u ? i : 0) * NU;
-      const double* s = w.S + i * NR; const double* lam = w.LAM + i * NR; double* ds = w.DS + i * NR;
-      const double* rec = w.REC + (size_t)i * RECSZ;
+      const double* dx = gDX() + i * NX; const double* du = gDU() + (has_u ? i : 0) * NU;
+      const double* s = gS() + i * NR; const double* lam = gLAM() + i * NR; double* ds = gDS() + i * NR;
+      const double* rec = gREC() + (size_t)i * RECSZ;
       double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
       auto row = [&](int r, double dsr) {
         const double sv = s[r], lv = lam[r];
@@ -1385,9 +1431,9 @@ struct Solver {
         gd += rec[Q_GC + 32 + IQ + v] * dx[IQ + v];
       } else if (role == 8) {
         // explicit rows: the solve returned the new multiplier w; ds follows from s dlam + lam ds = mu - s lam
-        if (mask & (1ull << R_LYAP)) { const double sv = s[R_LYAP], lv = lam[R_LYAP]; row(R_LYAP, mu / lv - sv - sv / lv * (w.DW[i * NW] - lv)); }
+        if (mask & (1ull << R_LYAP)) { const double sv = s[R_LYAP], lv = lam[R_LYAP]; row(R_LYAP, mu / lv - sv - sv / lv * (gDW()[i * NW] - lv)); }
         else ds[R_LYAP] = 0.0;
-        if (mask & (1ull << R_HW)) { const double sv = s[R_HW], lv = lam[R_HW]; row(R_HW, mu / lv - sv - sv / lv * (w.DW[i * NW + 1] - lv)); }
+        if (mask & (1ull << R_HW)) { const double sv = s[R_HW], lv = lam[R_HW]; row(R_HW, mu / lv - sv - sv / lv * (gDW()[i * NW + 1] - lv)); }
         else ds[R_HW] = 0.0;
         if (mask & (1ull << R_PZ)) row(R_PZ, -rec[Q_RG + R_PZ] - dx[IP + 2]);
         else ds[R_PZ] = 0.0;
@@ -1430,6 +1476,7 @@ struct Solver {
   // ---- trial point (x + a dx, u + a du, s + a ds) for the line search: constraint violation theta, cost (with and
   // without the regularisation term), sum ln s, max unrelaxed violation.  CTA-wide like the eval pass.
   CMPC_HD void trial(double alpha, double* out) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
     TrialScratch* ts = reinterpret_cast<TrialScratch*>(sm.M);
     const double d = c.delta, m = in.mass, k1 = in.k1;
@@ -1437,7 +1484,7 @@ struct Solver {
       const int ns = (N + 1 - i0) < TCH ? (N + 1 - i0) : TCH;
       for (int t = tid; t < ns * 2; t += nt) {
         const int il = t >> 1, e = t & 1, i = i0 + il, o = i * NX + (e ? IPSR : IPSL);
-        const double psi = w.X[o] + alpha * w.DX[o];
+        const double psi = gX()[o] + alpha * gDX()[o];
         ts[il].cs[e] = cos(psi); ts[il].sn[e] = sin(psi);
       }
       par.sync();
@@ -1445,8 +1492,8 @@ struct Solver {
         const int il = t >> 3, v = t & 7, i = i0 + il;
         if (i >= N) continue;
         const int e = v >> 2, k = v & 3;
-        const double* X = w.X + i * NX; const double* DX = w.DX + i * NX;
-        const double* U = w.U + i * NU; const double* DU = w.DU + i * NU;
+        const double* X = gX() + i * NX; const double* DX = gDX() + i * NX;
+        const double* U = gU() + i * NU; const double* DU = gDU() + i * NU;
         const int po = e ? IPR : IPL;
         const double cs = ts[il].cs[e], sn = ts[il].sn[e];
         double cx, cy; corner(c, k, cx, cy);
@@ -1463,7 +1510,7 @@ struct Solver {
       for (int t = tid; t < ns * 11; t += nt) {
         const int il = t / 11, q = t - il * 11, i = i0 + il;
         if (i >= N) continue;
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         const double (*pt)[7] = ts[il].part;
         double s = 0.0;
         if (q < 6) { const int e = q / 3, j = q - 3 * e; for (int k = 0; k < 4; ++k) s += pt[4 * e + k][j]; }
@@ -1476,12 +1523,12 @@ struct Solver {
         const int role = t / ns, il = t - role * ns, i = i0 + il;
         const bool has_u = i < N;
         TrialScratch& E = ts[il];
-        const double* X = w.X + i * NX; const double* DX = w.DX + i * NX;
-        const double* U = w.U + (has_u ? i : 0) * NU; const double* DU = w.DU + (has_u ? i : 0) * NU;
-        const double* Xn = w.X + (has_u ? i + 1 : i) * NX; const double* DXn = w.DX + (has_u ? i + 1 : i) * NX;
-        const double* S = w.S + i * NR; const double* DS = w.DS + i * NR;
+        const double* X = gX() + i * NX; const double* DX = gDX() + i * NX;
+        const double* U = gU() + (has_u ? i : 0) * NU; const double* DU = gDU() + (has_u ? i : 0) * NU;
+        const double* Xn = gX() + (has_u ? i + 1 : i) * NX; const double* DXn = gDX() + (has_u ? i + 1 : i) * NX;
+        const double* S = gS() + i * NR; const double* DS = gDS() + i * NR;
         const uint64_t mask = sm.mask[i];
-        const double gl = in.gamma[2 * i], gr = in.gamma[2 * i + 1];
+        const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         double theta = 0.0, cost = 0.0, cref = 0.0, lns = 0.0, viol = 0.0;
         auto row = [&](int r, double g) {
           const double st = S[r] + alpha * DS[r];
@@ -1505,7 +1552,7 @@ struct Solver {
             cost += (ge * c.w_sym + (1.0 - ge) * c.w_swing) * p[6];
             if (i >= 1) {
               const double dz = f2 - (X[IQ + v] + alpha * DX[IQ + v]);
-              cost += c.w_rate * in.gamma[2 * (i - 1) + e] * dz * dz;
+              cost += c.w_rate * i_gamma()[2 * (i - 1) + e] * dz * dz;
             }
             cref = cost;
             defect(IQ + v, f2);
@@ -1515,12 +1562,12 @@ struct Solver {
 #pragma unroll
           for (int j = 0; j < 12; ++j) x[j] = X[j] + alpha * DX[j];
           if (i >= 1) {
-            const double* ref = in.com_ref + 9 * (i - 1);
+            const double* ref = i_com_ref() + 9 * (i - 1);
             cost += c.w_xy * ((x[0] - ref[0]) * (x[0] - ref[0]) + (x[1] - ref[1]) * (x[1] - ref[1])) + wz_of(c, i - 1) * (x[2] - ref[2]) * (x[2] - ref[2]);
           }
           if (mask & (1ull << R_PZ)) row(R_PZ, x[IP + 2] - c.pz_max);
           if (has_u) {
-            const double* ref = in.com_ref + 9 * i;
+            const double* ref = i_com_ref() + 9 * i;
             double F[3], xph[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) { F[j] = gl * E.sum[j] + gr * E.sum[3 + j]; xph[j] = x[IH + j] + d * E.sum[6 + j]; }
@@ -1553,7 +1600,7 @@ struct Solver {
           }
           cref = cost;
         } else {
-          const double* fr = in.foot_ref + 8 * (i >= 1 ? i - 1 : 0);
+          const double* fr = i_foot_ref() + 8 * (i >= 1 ? i - 1 : 0);
           double creg = 0.0;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -1595,6 +1642,7 @@ struct Solver {
   }
 
   CMPC_HD void reduce_trial(double* out) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N;
     double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
     for (int i = 0; i <= N; ++i) {
@@ -1606,18 +1654,19 @@ struct Solver {
   }
 
   CMPC_HD void apply_step(double alpha, double a_d) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N, tid = par.tid(), nt = par.nt();
-    for (int t = tid; t < (N + 1) * NX; t += nt) { w.X[t] += alpha * w.DX[t]; w.Y[t] += alpha * (w.YN[t] - w.Y[t]); }
-    for (int t = tid; t < N * NU; t += nt) w.U[t] += alpha * w.DU[t];
+    for (int t = tid; t < (N + 1) * NX; t += nt) { gX()[t] += alpha * gDX()[t]; gY()[t] += alpha * (gYN()[t] - gY()[t]); }
+    for (int t = tid; t < N * NU; t += nt) gU()[t] += alpha * gDU()[t];
     for (int t = tid; t < (N + 1) * NR; t += nt) {
       const int i = t / NR, r = t % NR;
       if (!(sm.mask[i] & (1ull << r))) continue;
-      const double s0 = w.S[t], l0 = w.LAM[t], dsr = w.DS[t];
+      const double s0 = gS()[t], l0 = gLAM()[t], dsr = gDS()[t];
       const double dl = -l0 + mu / s0 - l0 / s0 * dsr;
       double sn = s0 + alpha * dsr, ln = l0 + a_d * dl;
       const double lo = mu / (1e10 * sn), hi = 1e10 * mu / sn;       // IPOPT eq. (16)
       ln = ln < lo ? lo : (ln > hi ? hi : ln);
-      w.S[t] = sn; w.LAM[t] = ln;
+      gS()[t] = sn; gLAM()[t] = ln;
     }
     par.sync();
   }
@@ -1627,6 +1676,7 @@ struct Solver {
   // from the solver's own cold start, a failed cold solve again with a ten times larger, then a ten times smaller initial barrier (other central paths).
   // ---- per-solve tables: structural pattern of [B A], Lyapunov constants and scatter table, tile map
   CMPC_HD void setup() {
+    Smem& sm = par.template smem<Smem>();
     if (par.tid() == 0) {                                  // structural pattern of [B A]: by column (ba_row) and by row (gather)
       int n = 0;
       for (int t = 0; t < NZ * 4; ++t) sm.barow[t] = (signed char)ba_row(t >> 2, t & 3);
@@ -1692,6 +1742,7 @@ struct Solver {
 
   // ---- the interior-point loop
   CMPC_HD void run_once(int warm, Stats* st) {
+    Smem& sm = par.template smem<Smem>();
     const int N = c.N;
     double pviol;
     if (par.tid() == 0) { build_masks(c, in, sm.mask, &pviol); sm.red[0] = pviol; }
@@ -1708,9 +1759,9 @@ struct Solver {
     // merit quantities of the current point (constraint violation theta, cost, sum ln s): evaluated once here, afterwards
     // they are the values of the accepted trial point -- the eval pass needs no logarithms
     double cur[5];
-    for (int t = par.tid(); t < (N + 1) * NX; t += par.nt()) w.DX[t] = 0.0;
-    for (int t = par.tid(); t < N * NU; t += par.nt()) w.DU[t] = 0.0;
-    for (int t = par.tid(); t < (N + 1) * NR; t += par.nt()) w.DS[t] = 0.0;
+    for (int t = par.tid(); t < (N + 1) * NX; t += par.nt()) gDX()[t] = 0.0;
+    for (int t = par.tid(); t < N * NU; t += par.nt()) gDU()[t] = 0.0;
+    for (int t = par.tid(); t < (N + 1) * NR; t += par.nt()) gDS()[t] = 0.0;
     par.sync();
     trial(0.0, cur);
     eval(ev);
@@ -1789,9 +1840,9 @@ struct Solver {
     }
     // final report: reference cost (no eps_reg term) and max unrelaxed violation incl. dynamics defects
     double tr[5];
-    for (int t = par.tid(); t < (N + 1) * NX; t += par.nt()) w.DX[t] = 0.0;
-    for (int t = par.tid(); t < N * NU; t += par.nt()) w.DU[t] = 0.0;
-    for (int t = par.tid(); t < (N + 1) * NR; t += par.nt()) w.DS[t] = 0.0;
+    for (int t = par.tid(); t < (N + 1) * NX; t += par.nt()) gDX()[t] = 0.0;
+    for (int t = par.tid(); t < N * NU; t += par.nt()) gDU()[t] = 0.0;
+    for (int t = par.tid(); t < (N + 1) * NR; t += par.nt()) gDS()[t] = 0.0;
     par.sync();
     trial(0.0, tr);
     if (status == ST_CONVERGED && pviol > 1e-6) status = ST_INFEASIBLE_X0;

@@ -12,6 +12,9 @@
 using namespace cmpc;
 
 struct ParSerial {
+  void* smem_ptr = nullptr;
+  template <class T> T& smem() const { return *static_cast<T*>(smem_ptr); }
+  void bind(void* p) { smem_ptr = p; }
   int tid() const { return 0; }
   int nt() const { return 1; }
   void sync() const {}
