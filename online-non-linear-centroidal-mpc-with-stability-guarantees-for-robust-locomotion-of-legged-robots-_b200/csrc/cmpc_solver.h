@@ -1088,7 +1088,7 @@ struct Solver {
         }
         bool okp = true;
         // factor a diagonal tile held in registers; publish {1/d0..1/d3, l10, l20, l21, l30, l31, l32} and the pivot test
-        auto diag_tile = [&](double* t, int tk) {
+        auto diag_tile = [&](double (&t)[16], int tk) {
           const double p0 = t[0];
           const double i0 = cmpc_rsqrt(p0);
           const double l10 = t[4] * i0, l20 = t[8] * i0, l30 = t[12] * i0;
@@ -1112,7 +1112,7 @@ struct Solver {
           t[12] = l30; t[13] = l31; t[14] = l32; t[15] = p3 * i3;
         };
         // rows of L of a tile below the diagonal tile (in place), published as tile row `ti` of the panel
-        auto panel_tile = [&](double* t, int ti) {
+        auto panel_tile = [&](double (&t)[16], int ti) {
           const double* d = sm.dpub;
           const double i0 = d[0], i1 = d[1], i2 = d[2], i3 = d[3], l10 = d[4], l20 = d[5], l21 = d[6], l30 = d[7], l31 = d[8], l32 = d[9];
           double* pl = (sm.W + 128) + PSTR * ti;

@@ -13,18 +13,19 @@ from test_gpu_closed_loop import _oracle_mpc
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 t_end = int(sys.argv[2]) if len(sys.argv) > 2 else 1970 - N
+over = {k: float(v) for k, v in (a.split("=") for a in sys.argv[3:])}       # solver option overrides of the GPU side (experiments)
 res = {}
 for which in ("gpu", "oracle"):
     planner, com_ref, params, initial = load_walk()
     params["N"] = N
-    mpc = centroidal_mpc(initial, planner, params, com_ref, None, None) if which == "gpu" else _oracle_mpc(initial, planner, params, com_ref)
+    mpc = centroidal_mpc(initial, planner, params, com_ref, None, None, **over) if which == "gpu" else _oracle_mpc(initial, planner, params, com_ref)
     its = []
     t0 = time.time()
     traj = surrogate_walk(mpc, initial, 0, t_end, params["mass"], hw_trace=initial["hw_meas"],
                           record=lambda t, m, cur: its.append(m.last_iters if which == "gpu" else m.last.iters))
     res[which] = dict(traj=traj, secs=time.time() - t0, iters=float(np.mean(its)), plan=np.array([s["pos"] for s in planner.plan]))
 a, b = res["gpu"]["traj"], res["oracle"]["traj"]
-print(json.dumps({"N": N, "ticks": int(t_end), "max_com_pos_dev_m": float(np.abs(a[:, 0:3] - b[:, 0:3]).max()),
+print(json.dumps({"N": N, "ticks": int(t_end), "overrides": over, "max_com_pos_dev_m": float(np.abs(a[:, 0:3] - b[:, 0:3]).max()),
                   "max_com_vel_dev": float(np.abs(a[:, 3:6] - b[:, 3:6]).max()), "max_theta_hat_dev": float(np.abs(a[:, 9:12] - b[:, 9:12]).max()),
                   "max_plan_dev_m": float(np.abs(res["gpu"]["plan"] - res["oracle"]["plan"]).max()),
                   "gpu_s_per_tick": res["gpu"]["secs"] / t_end, "oracle_s_per_tick": res["oracle"]["secs"] / t_end,
