@@ -134,3 +134,30 @@ def test_batch_capacity_and_empty(pkg, golden):
         s.solve_host(g["x0"][:3], g["com_ref"][:3], g["foot_ref"][:3], g["gamma"][:3], 40.0, 4.0, 0)
     one = s.solve_host(g["x0"][:1], g["com_ref"][:1], g["foot_ref"][:1], g["gamma"][:1], float(g["mass"]), float(g["k1"]), 0)
     assert one["status"][0] == 0
+
+
+def test_solves_are_deterministic_and_independent_of_batch_order(pkg, walk_ticks):
+    """The same instance gives bit-identical results run after run, warm or cold, wherever it sits in the batch and in
+    whatever order the CTAs are launched (a data race or an uninitialised read in the kernel would show up here;
+    compute-sanitizer is not available on the GPU pool)."""
+    N, B = 20, 600                                            # more instances than the 592 resident CTA slots
+    w = walk_ticks[N]
+    rng = np.random.default_rng(5)
+    idx = rng.integers(1, len(w["x0"]), B)
+    arg = lambda ii: (w["x0"][ii], w["com_ref"][ii], w["foot_ref"][ii], w["gamma"][ii], float(w["mass"]), float(w["k1"]))
+    keys = ("x1", "u0", "xN", "cost", "viol", "status", "iters")
+
+    def run(order):
+        s = pkg.BatchSolver(N, B, device=0)
+        cold = s.solve_host(*arg(idx[order] - 1), 0)
+        warm = s.solve_host(*arg(idx[order]), 2)                 # launch order = work of the cold solves
+        s.close()
+        inv = np.argsort(order)
+        return [{k: np.array(o[k])[inv] for k in keys} for o in (cold, warm)]
+
+    ident = np.arange(B)
+    a, b, c = run(ident), run(ident), run(rng.permutation(B))
+    for first, other in ((a, b), (a, c)):
+        for o1, o2 in zip(first, other):
+            for k in keys:
+                assert np.array_equal(o1[k], o2[k]), k
