@@ -6,6 +6,7 @@ Layout
   _lib.py          ctypes binding of the C ABI (`BatchSolver`)
   assembly.py      per-tick parameter assembly of `solve` (MPC file :482-600), vectorised
   fleet.py         batched closed loop on the device: table-gather assembly, solve, plant, step adjustment
+  com_reference.py CoM reference tables of `functions.references` without CasADi (minimum-norm quintic spline)
   parallel.py      instance sharding over GPUs + statistics reduction (no collective on the hot path)
   centroidal_mpc_vertices.py / centroidal_mpc_vertices_payload.py
                    drop-in modules with the reference's `centroidal_mpc` class surface
@@ -16,6 +17,8 @@ from ._lib import BatchSolver, CmpcError, build_library, library_path, measure_f
 from .assembly import PlanTables, assemble_tick, pack_instances  # noqa: F401
 from .parallel import gather_stats, shard_arrays, shard_range  # noqa: F401
 from .fleet import Fleet  # noqa: F401
+from .com_reference import quintic_coefficients, references_from_knots, sample_tables  # noqa: F401
 
 __all__ = ["BatchSolver", "CmpcError", "build_library", "library_path", "measure_fp64_peak",
-           "PlanTables", "assemble_tick", "pack_instances", "gather_stats", "shard_arrays", "shard_range", "Fleet"]
+           "PlanTables", "assemble_tick", "pack_instances", "gather_stats", "shard_arrays", "shard_range", "Fleet",
+           "quintic_coefficients", "references_from_knots", "sample_tables"]
