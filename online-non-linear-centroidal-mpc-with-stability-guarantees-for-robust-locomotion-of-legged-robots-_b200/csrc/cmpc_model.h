@@ -68,7 +68,7 @@ CMPC_HD Config default_config(int N) {
   c.relax = 1e-8;
   c.mu_init = 0.1; c.mu_final = 1e-9; c.tol = 1e-8; c.kappa_eps = 10.0; c.kappa_mu = 0.2;
   c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 1e-6; c.warm_comp = 0.0;
-  c.max_iter = 100; c.ls_max = 3;
+  c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
   return c;
 }
 

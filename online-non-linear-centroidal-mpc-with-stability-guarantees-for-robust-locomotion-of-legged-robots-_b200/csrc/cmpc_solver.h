@@ -36,7 +36,8 @@ constexpr int FACSZ = F_PV + NX;            // 1798 doubles
 constexpr int FWDBUF = KSZ + NX;            // forward sweep staging of one stage: K | k | d
 constexpr int NTILE = 15 * 16 / 2;          // 4 x 4 tiles of the padded 64 x 64 lower triangle right of tile column 0 (120)
 constexpr int NLY = 33 + 3 * 66;               // entries of the stage block the Lyapunov row touches: 33 gradient + 198 same-axis pairs
-constexpr int PSTR = 17;                    // doubles between tile rows of the pivot panel (odd: lanes with different tile rows hit different banks)
+constexpr int PSTR = 18;                    // doubles between tile rows of the pivot panel: 16-byte aligned (128-bit accesses), 8 distinct bank groups
+struct alignas(16) Pair { double x, y; };   // two panel entries moved by one 128-bit shared-memory access
 // per-stage derivative record written by the eval pass
 constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 448, Q_FRIC = 508,
               Q_LG = 556, Q_LC = 568, Q_LSIG = 584, Q_HP = 585, Q_HLAM = 588, Q_HSIG = 589, Q_YH = 590,
@@ -1066,6 +1067,8 @@ struct Solver {
       //   2. the owners of the tiles below it form their rows of L (4 x 4 forward substitution, registers) and
       //      publish the 64 x 4 panel                                                         -- barrier B
       //   3. every tile to the right applies the rank-4 update (64 FMAs fed by 32 shared loads).
+      // The panel is stored column by column (four values per column and tile row): the update is four rank-1 steps, each
+      // streaming one column of L for the tile's rows and columns (128-bit loads), eight operand registers next to the tile.
       // (the panel and the pivot-column buffer live in the W storage, idle between the P [B A] products and the gains.)
       // The two explicit multipliers (columns 32, 33; pivot sign -1) follow column by column.  The gradient row
       // (row 62) is carried along.  Inputs without coupling at a stage (stance-foot velocities, swing-foot
@@ -1123,7 +1126,12 @@ struct Solver {
             const double v2 = (t[4 * a_ + 2] - v0 * l20 - v1 * l21) * i2;
             const double v3 = (t[4 * a_ + 3] - v0 * l30 - v1 * l31 - v2 * l32) * i3;
             t[4 * a_] = v0; t[4 * a_ + 1] = v1; t[4 * a_ + 2] = v2; t[4 * a_ + 3] = v3;
-            pl[4 * a_] = v0; pl[4 * a_ + 1] = v1; pl[4 * a_ + 2] = v2; pl[4 * a_ + 3] = v3;
+          }
+          // published column by column (pl[4 kk + a]): the update then streams one column of L per rank-1 step
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            reinterpret_cast<Pair*>(pl)[2 * kk] = Pair{t[kk], t[4 + kk]};
+            reinterpret_cast<Pair*>(pl)[2 * kk + 1] = Pair{t[8 + kk], t[12 + kk]};
           }
         };
         {   // ---- block 0: tile column 0 (transient tiles)
@@ -1178,27 +1186,23 @@ struct Solver {
           for (int sl = 0; sl < Par::TPT; ++sl) {
             const int ti = ti_[sl], tj = tj_[sl];
             if (tj <= tk) continue;                                  // (no tile: tj = 0) tiles left of / in the block: final
-            const double* pr = (sm.W + 128) + PSTR * ti;
-            if (ti == tj) {
-              double lr[16];
+            const Pair* pr = reinterpret_cast<const Pair*>((sm.W + 128) + PSTR * ti);
+            const Pair* pc = reinterpret_cast<const Pair*>((sm.W + 128) + PSTR * tj);
+            // four rank-1 steps, one column of the panel each: eight operand registers live next to the tile
 #pragma unroll
-              for (int q = 0; q < 16; ++q) lr[q] = pr[q];
-#pragma unroll
-              for (int a_ = 0; a_ < 4; ++a_)
-#pragma unroll
-                for (int b_ = 0; b_ <= a_; ++b_)
-                  T[sl][4 * a_ + b_] -= lr[4 * a_] * lr[4 * b_] + lr[4 * a_ + 1] * lr[4 * b_ + 1] + lr[4 * a_ + 2] * lr[4 * b_ + 2] + lr[4 * a_ + 3] * lr[4 * b_ + 3];
-            } else {
-              const double* pc = (sm.W + 128) + PSTR * tj;
-              double lr[16];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) lr[q] = pr[q];
-#pragma unroll
-              for (int b_ = 0; b_ < 4; ++b_) {
-                const double v0 = pc[4 * b_], v1 = pc[4 * b_ + 1], v2 = pc[4 * b_ + 2], v3 = pc[4 * b_ + 3];
+            for (int kk = 0; kk < 4; ++kk) {
+              const Pair r01 = pr[2 * kk], r23 = pr[2 * kk + 1], c01 = pc[2 * kk], c23 = pc[2 * kk + 1];
+              const double lr[4] = {r01.x, r01.y, r23.x, r23.y}, lc[4] = {c01.x, c01.y, c23.x, c23.y};
+              if (ti == tj) {
 #pragma unroll
                 for (int a_ = 0; a_ < 4; ++a_)
-                  T[sl][4 * a_ + b_] -= lr[4 * a_] * v0 + lr[4 * a_ + 1] * v1 + lr[4 * a_ + 2] * v2 + lr[4 * a_ + 3] * v3;
+#pragma unroll
+                  for (int b_ = 0; b_ <= a_; ++b_) T[sl][4 * a_ + b_] -= lr[a_] * lc[b_];
+              } else {
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                  for (int b_ = 0; b_ < 4; ++b_) T[sl][4 * a_ + b_] -= lr[a_] * lc[b_];
               }
             }
           }
