@@ -258,6 +258,20 @@ def main():
         torch.cuda.synchronize()
         kms.append(solver.last_stats()["kernel_ms"])
     kernel_ms = float(np.mean(kms))
+    # ------------------------------------------------------------------ single-instance latency (one robot, one tick)
+    lat = None
+    if rank == 0:
+        one = pkg.BatchSolver(N, 1, device=local, **over)
+        ms = []
+        for k in range(48):                                              # 48 different ticks, each warm-started from its previous tick
+            sl = slice(k, k + 1)
+            one.solve_host(*[x[sl] for x in prev], mass, k1, 0)
+            t0 = time.perf_counter()
+            r1 = one.solve_host(*[x[sl] for x in cur], mass, k1, 2)      # host buffers in, host buffers out: what the drop-in class does
+            ms.append((time.perf_counter() - t0) * 1e3)
+        one.close()
+        lat = {"p50_ms": float(np.percentile(ms, 50)), "p90_ms": float(np.percentile(ms, 90)), "max_ms": float(np.max(ms)),
+               "what": "cmpc_solve_host of ONE instance (H2D + kernel + D2H), full warm start, 48 ticks of the replay"}
     # ------------------------------------------------------------------ e2e through the host-buffer C-ABI call
     for _ in range(min(W, 2)):
         solver.warm_restore(B); res = solver.solve_host(*cur, mass, k1, 2)
@@ -318,7 +332,7 @@ def main():
             "data": "synthetic (recorded surrogate walk, tests/golden/walk_ticks_N%d.npz)" % N, "config": config,
             "converged_fraction": conv_all / (B * world), "iters_per_solve": iters_all / (B * world),
             "factorisations_per_solve": nfact_all / (B * world),
-            "p50_batch_latency_ms": total_ms / K,
+            "p50_batch_latency_ms": total_ms / K, "single_instance_latency": lat,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": 2 * K * world, "roofline": roofline, "clocks": clocks}
     if world == 1 and not a.no_cpu_baseline:
