@@ -128,6 +128,8 @@ struct alignas(16) Smem {
   short csr_ptr[NX + 1];      // structural pattern of [B A] by rows (gather form)
   unsigned char csr_idx[NZ * 4];
   signed char barow[NZ * 4];  // ba_row(j, q) table
+  unsigned short baofs[NZ * 4];  // row offset ba_row * NZ into W of slot (j, q), 0 for an empty slot (whose [B A] value is 0)
+  unsigned char barz[NZ * 4];    // ba_row with 0 for an empty slot
   unsigned short ly_m[NLY], ly_s[NLY];   // Lyapunov row scatter table: index into M, index of the coefficient in the record
   unsigned char ly_g[NLY];               // ... and the two gamma selectors (0: left, 1: right, 2: none), 4 bits each
 };
@@ -900,7 +902,7 @@ struct Solver {
     for (int j = lane; j < NZ; j += nl) {
       int rr[4]; double bv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const int r0 = sm.barow[4 * j + q]; bv[q] = r0 >= 0 ? bav[4 * j + q] : 0.0; rr[q] = r0 >= 0 ? r0 : 0; }
+      for (int q = 0; q < 4; ++q) { bv[q] = bav[4 * j + q]; rr[q] = sm.barz[4 * j + q]; }       // (empty slots hold 0 in the record)
       for (int r = wid; r < NX; r += nw) {
         const double* Pr = sm.P + r * NX;
         sm.W[r * NZ + j] = (Pr[rr[0]] * bv[0] + Pr[rr[1]] * bv[1]) + (Pr[rr[2]] * bv[2] + Pr[rr[3]] * bv[3]);
@@ -1041,7 +1043,7 @@ struct Solver {
           int rr[4]; double bv[4];
           if (sm.barow[4 * a_] < 0) continue;                    // structurally empty column (previous-f_z states)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { const int r0 = sm.barow[4 * a_ + q]; bv[q] = r0 >= 0 ? bav[4 * a_ + q] : 0.0; rr[q] = (r0 >= 0 ? r0 : 0) * NZ; }
+          for (int q = 0; q < 4; ++q) { bv[q] = bav[4 * a_ + q]; rr[q] = sm.baofs[4 * a_ + q]; }
           double* Mr = sm.M + mi(mz(a_), 0);
           for (int b_ = lane; b_ <= a_; b_ += nl) {
             const double s = (bv[0] * sm.W[rr[0] + b_] + bv[1] * sm.W[rr[1] + b_]) + (bv[2] * sm.W[rr[2] + b_] + bv[3] * sm.W[rr[3] + b_]);
@@ -1684,6 +1686,7 @@ struct Solver {
     if (par.tid() == 0) {                                  // structural pattern of [B A]: by column (ba_row) and by row (gather)
       int n = 0;
       for (int t = 0; t < NZ * 4; ++t) sm.barow[t] = (signed char)ba_row(t >> 2, t & 3);
+      for (int t = 0; t < NZ * 4; ++t) { const int r0 = sm.barow[t] >= 0 ? sm.barow[t] : 0; sm.barz[t] = (unsigned char)r0; sm.baofs[t] = (unsigned short)(r0 * NZ); }
       for (int r = 0; r < NX; ++r) {
         sm.csr_ptr[r] = (short)n;
         for (int t = 0; t < NZ * 4; ++t) if (sm.barow[t] == r) sm.csr_idx[n++] = (unsigned char)t;
