@@ -1535,10 +1535,11 @@ struct Solver {
         const double* S = gS() + i * NR; const double* DS = gDS() + i * NR;
         const uint64_t mask = sm.mask[i];
         const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
-        double theta = 0.0, cost = 0.0, cref = 0.0, lns = 0.0, viol = 0.0;
+        double theta = 0.0, cost = 0.0, cref = 0.0, viol = 0.0;
+        double sprod = 1.0, smin_t = 1.0;                          // sum ln s of the item's rows (<= 12) as one logarithm of their product
         auto row = [&](int r, double g) {
           const double st = S[r] + alpha * DS[r];
-          theta += fabs(g - c.relax + st); lns += log(st); viol = g > viol ? g : viol;
+          theta += fabs(g - c.relax + st); sprod *= st; smin_t = st < smin_t ? st : smin_t; viol = g > viol ? g : viol;
         };
         auto defect = [&](int r, double xp) {
           const double ad = fabs(xp - (Xn[r] + alpha * DXn[r]));
@@ -1630,7 +1631,7 @@ struct Solver {
           cref = cost; cost += creg;
         }
         double* st = E.st[role];
-        st[0] = theta; st[1] = cost; st[2] = lns; st[3] = viol; st[4] = cref;
+        st[0] = theta; st[1] = cost; st[2] = log(smin_t > 0.0 ? sprod : -1.0); st[3] = viol; st[4] = cref;      // NaN if a slack left the domain
       }
       par.sync();
       for (int il = tid; il < ns; il += nt) {
