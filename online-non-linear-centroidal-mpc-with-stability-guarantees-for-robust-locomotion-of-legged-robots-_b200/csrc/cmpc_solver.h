@@ -78,6 +78,20 @@ CMPC_HD double cmpc_rcp(double x) {
 #endif
 }
 
+// Branch-free reciprocal square root for pivots (1e-14 < x < 1e30): single-precision seed, two Newton steps in double.
+// Unlike rsqrt(double) it has no range check / slow-path branch, so two of them interleave in one instruction stream.
+CMPC_HD double cmpc_rsqrt_nb(double x) {
+#if defined(__CUDA_ARCH__)
+  double y = (double)rsqrtf((float)x);
+  const double h = 0.5 * x;
+  y = y * fma(-h, y * y, 1.5);
+  y = y * fma(-h, y * y, 1.5);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 CMPC_HD double cmpc_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
   return rsqrt(x);
@@ -1094,17 +1108,22 @@ struct Solver {
         bool okp = true;
         // factor a diagonal tile held in registers; publish {1/d0..1/d3, l10, l20, l21, l30, l31, l32} and the pivot test
         auto diag_tile = [&](double (&t)[16], int tk) {
+          // two 2 x 2 steps: in each, rsqrt(a) and rsqrt(a c - b^2) are independent and branch-free, so they interleave and
+          // the dependent chain holds two rsqrt latencies instead of four (second pivot of a step = (a c - b^2) / a, its
+          // reciprocal root = a rsqrt(a) rsqrt(a c - b^2))
           const double p0 = t[0];
-          const double i0 = cmpc_rsqrt(p0);
+          const double det1 = p0 * t[5] - t[4] * t[4];
+          const double i0 = cmpc_rsqrt_nb(p0), r1 = cmpc_rsqrt_nb(det1);
+          const double p1 = det1 * (i0 * i0), i1 = r1 * (p0 * i0);
           const double l10 = t[4] * i0, l20 = t[8] * i0, l30 = t[12] * i0;
-          const double p1 = t[5] - l10 * l10;
-          const double i1 = cmpc_rsqrt(p1);
           const double l21 = (t[9] - l20 * l10) * i1, l31 = (t[13] - l30 * l10) * i1;
           const double p2 = t[10] - l20 * l20 - l21 * l21;
-          const double i2 = cmpc_rsqrt(p2);
-          const double l32 = (t[14] - l30 * l20 - l31 * l21) * i2;
-          const double p3 = t[15] - l30 * l30 - l31 * l31 - l32 * l32;
-          const double i3 = cmpc_rsqrt(p3);
+          const double b2 = t[14] - l30 * l20 - l31 * l21;
+          const double c2 = t[15] - l30 * l30 - l31 * l31;
+          const double det2 = p2 * c2 - b2 * b2;
+          const double i2 = cmpc_rsqrt_nb(p2), r3 = cmpc_rsqrt_nb(det2);
+          const double p3 = det2 * (i2 * i2), i3 = r3 * (p2 * i2);
+          const double l32 = b2 * i2;
           const bool good = p0 > 1e-14 && p1 > 1e-14 && p2 > 1e-14 && p3 > 1e-14;
 #ifdef CMPC_TRACE
           if (cmpc_trace_on && !good) printf("   pivot fail stage %d block %d piv %.3e %.3e %.3e %.3e reg %.1e\n", i, tk, p0, p1, p2, p3, reg);
