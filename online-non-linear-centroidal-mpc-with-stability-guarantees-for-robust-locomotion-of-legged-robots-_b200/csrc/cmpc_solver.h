@@ -1817,7 +1817,7 @@ struct Solver {
         ++nreg;
         if (reg == 0.0) reg = (reg_last == 0.0) ? 1e-4 : (reg_last / 3.0 > 1e-20 ? reg_last / 3.0 : 1e-20);
         else reg *= (reg_last == 0.0) ? 100.0 : 8.0;
-        if (reg > 1e20) break;
+        if (reg > 1e12) break;                              // (keeps the pivots inside the range of the single-precision rsqrt seed)
       }
       if (!ok) { status = ST_REGULARIZATION; break; }
       if (reg > 0.0) reg_last = reg;
