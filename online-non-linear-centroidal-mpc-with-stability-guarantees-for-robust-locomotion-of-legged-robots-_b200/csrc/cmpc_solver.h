@@ -70,6 +70,16 @@ static double cmpc_dbg_rd[64];
 #endif
 
 
+CMPC_HD int cmpc_popcount(uint64_t m) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(m);
+#else
+  int n = 0;
+  while (m) { n += (int)(m & 1ull); m >>= 1; }
+  return n;
+#endif
+}
+
 CMPC_HD double cmpc_rcp(double x) {
 #if defined(__CUDA_ARCH__)
   return __drcp_rn(x);
@@ -876,7 +886,7 @@ struct Solver {
   CMPC_HD int n_rows_total() const {
     Smem& sm = par.template smem<Smem>();
     int n = 0;
-    for (int i = 0; i <= c.N; ++i) { uint64_t m = sm.mask[i]; while (m) { n += (int)(m & 1ull); m >>= 1; } }
+    for (int i = 0; i <= c.N; ++i) n += cmpc_popcount(sm.mask[i]);
     return n;
   }
 
@@ -1703,15 +1713,20 @@ struct Solver {
   // ---- per-solve tables: structural pattern of [B A], Lyapunov constants and scatter table, tile map
   CMPC_HD void setup() {
     Smem& sm = par.template smem<Smem>();
-    if (par.tid() == 0) {                                  // structural pattern of [B A]: by column (ba_row) and by row (gather)
-      int n = 0;
-      for (int t = 0; t < NZ * 4; ++t) sm.barow[t] = (signed char)ba_row(t >> 2, t & 3);
-      for (int t = 0; t < NZ * 4; ++t) { const int r0 = sm.barow[t] >= 0 ? sm.barow[t] : 0; sm.barz[t] = (unsigned char)r0; sm.baofs[t] = (unsigned short)(r0 * NZ); }
-      for (int r = 0; r < NX; ++r) {
-        sm.csr_ptr[r] = (short)n;
-        for (int t = 0; t < NZ * 4; ++t) if (sm.barow[t] == r) sm.csr_idx[n++] = (unsigned char)t;
-      }
-      sm.csr_ptr[NX] = (short)n;
+    // structural pattern of [B A]: by column (ba_row) and by row (gather), built by the whole CTA
+    for (int t = par.tid(); t < NZ * 4; t += par.nt()) {
+      const int r0 = ba_row(t >> 2, t & 3);
+      sm.barow[t] = (signed char)r0;
+      sm.barz[t] = (unsigned char)(r0 >= 0 ? r0 : 0); sm.baofs[t] = (unsigned short)((r0 >= 0 ? r0 : 0) * NZ);
+    }
+    par.sync();
+    for (int r = par.tid(); r < NX; r += par.nt()) {            // entries of row r, and the number of entries in the rows before it
+      int before = 0, n = 0;
+      for (int t = 0; t < NZ * 4; ++t) { const int rr = sm.barow[t]; before += (rr >= 0 && rr < r); n += (rr == r); }
+      sm.csr_ptr[r] = (short)before;
+      if (r == NX - 1) sm.csr_ptr[NX] = (short)(before + n);
+      int k = before;
+      for (int t = 0; t < NZ * 4; ++t) if (sm.barow[t] == r) sm.csr_idx[k++] = (unsigned char)t;
     }
     if (par.tid() == 0) lyapunov_consts(c, in, sm.lyapC);
     // Lyapunov row: which entries of the stage block it touches, with which coefficient.  Touched variable a (0..32):
