@@ -479,6 +479,18 @@ struct Solver {
         gX()[i * NX + IQ + v] = (i >= 1) ? gU()[(i - 1) * NU + 3 * v + 2] : 0.0;
       }
     }
+    if (warm == 4) {
+      // automatic: shift when a contact switch lies inside the horizon (it moves one stage per tick, so the previous tick's
+      // stage i + 1 is the better start for stage i), else keep the stage alignment (references move 1.5 mm per tick)
+      bool sw = false;
+      const int kind = (int)c.xp[1];
+      for (int i = 1; i <= N; ++i) {
+        const double a0 = i_gamma()[2 * i - 2], a1 = i_gamma()[2 * i - 1], b0 = i_gamma()[2 * i], b1 = i_gamma()[2 * i + 1];
+        if (kind == 0) sw = sw || (b0 > a0) || (b1 > a1);            // landing
+        else sw = sw || (b0 != a0) || (b1 != a1);                    // any switch
+      }
+      warm = sw ? 3 : 2;
+    }
     if (warm == 3) {
       // MPC shift: the previous tick's stage i+1 becomes this tick's stage i (the last stage is repeated).  Staged
       // through the step buffers so the in-place move is race free.
@@ -524,6 +536,24 @@ struct Solver {
         const int i = t / NR, r = t % NR;
         if (!(sm.mask[i] & (1ull << r))) { gS()[t] = 1.0; gLAM()[t] = 0.0; continue; }
         double sv = gS()[t], lv = gLAM()[t];
+        if (c.warm_new_push > 0.0 && sv == 1.0 && lv == 0.0) {
+          // the row was not part of the previous tick's problem at this stage (the contact schedule moved on): start its
+          // slack from the row's value at the warm point, like a cold start does, with the multiplier on the central path
+          double gv = 0.0;
+          if (r >= R_FRIC && r < R_UNI) {
+            const int v = (r - R_FRIC) >> 2, q = (r - R_FRIC) & 3;
+            const double* f = gU() + i * NU + 3 * v;
+            gv = ((q & 1) ? -1.0 : 1.0) * f[q >> 1] - c.mu_fric * f[2];
+          } else if (r >= R_UNI && r < R_BOX) {
+            gv = -gU()[i * NU + 3 * (r - R_UNI) + 2];
+          } else if (r >= R_BOX) {
+            const int e = (r - R_BOX) / 6, q = (r - R_BOX) % 6, j = q >> 1;
+            const double err = gX()[i * NX + (e ? IPR : IPL) + j] - i_foot_ref()[8 * (i - 1) + 3 * e + j];
+            gv = ((q & 1) ? -err : err) - c.box[j];
+          }
+          sv = c.relax - gv; sv = sv > c.warm_new_push ? sv : c.warm_new_push;
+          lv = mu / sv;
+        }
         if (!(sv > c.warm_push)) sv = c.warm_push;
         if (!(lv > mu / sv * 1e-3)) lv = mu / sv * 1e-3;
         if (c.warm_comp > 0.0 && lv > mu / sv * c.warm_comp) lv = mu / sv * c.warm_comp;
@@ -1440,7 +1470,11 @@ struct Solver {
         const double sv = s[r], lv = lam[r];
         ds[r] = dsr;
         const double dl = -lv + mu / sv - lv / sv * dsr;
-        if (dsr < 0.0) { const double a = -tau * sv / dsr; ap = a < ap ? a : ap; }
+        if (dsr < 0.0) { const double a = -tau * sv / dsr; ap = a < ap ? a : ap;
+#ifdef CMPC_TRACE
+          if (cmpc_trace_on > 1 && a < 0.9) printf("      a_p %.2e stage %d row %d s %.2e ds %.2e lam %.2e rg %.2e\n", a, i, r, sv, dsr, lv, r >= 2 ? rec[Q_RG + r] : 0.0);
+#endif
+        }
         if (dl < 0.0) { const double a = -tau * lv / dl; ad = a < ad ? a : ad; }
         dsos += dsr / sv;
       };
@@ -1700,6 +1734,7 @@ struct Solver {
       const double s0 = gS()[t], l0 = gLAM()[t], dsr = gDS()[t];
       const double dl = -l0 + mu / s0 - l0 / s0 * dsr;
       double sn = s0 + alpha * dsr, ln = l0 + a_d * dl;
+      if (c.xp[0] > 0.0) { ln = l0 + dl; const double fl = (1.0 - c.xp[0]) * l0; ln = ln < fl ? fl : ln; }
       const double lo = mu / (1e10 * sn), hi = 1e10 * mu / sn;       // IPOPT eq. (16)
       ln = ln < lo ? lo : (ln > hi ? hi : ln);
       gS()[t] = sn; gLAM()[t] = ln;

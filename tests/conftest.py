@@ -24,7 +24,8 @@ def golden():
     import numpy as np
     class Lazy(dict):
         def __missing__(self, N):
-            self[N] = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_N%d.npz" % N)))
+            name = "golden_N%d.npz" % N if isinstance(N, int) else "golden_%s.npz" % N
+            self[N] = dict(np.load(os.path.join(ROOT, "tests", "golden", name)))
             return self[N]
     return Lazy()
 

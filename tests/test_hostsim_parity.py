@@ -23,7 +23,9 @@ def problem(g, k, N):
     f = g["foot_ref"][k]
     p.pl_ref, p.pr_ref, p.al_ref, p.ar_ref = f[:, 0:3].T, f[:, 3:6].T, f[:, 6], f[:, 7]
     p.gl, p.gr = g["gamma"][k][:, 0], g["gamma"][k][:, 1]
-    p.mass, p.k1, p.eps_reg, p.w_rate = float(g["mass"]), float(g["k1"]), None, 1.0      # eps_reg: product default
+    per = np.ndim(g["mass"]) > 0                                   # round-2 golden files carry per-instance mass / k1
+    p.mass, p.k1 = (float(g["mass"][k]), float(g["k1"][k])) if per else (float(g["mass"]), float(g["k1"]))
+    p.eps_reg, p.w_rate = None, 1.0                               # eps_reg: product default
     return p
 
 
@@ -38,6 +40,19 @@ def test_core_matches_oracle_golden(golden, N):
         assert r["viol"] <= VIOL_TOL
         ec, ex, eu = golden_errors(g, k, r["cost"], r["X"][:20, 1], r["U"][:, 0])
         assert ec <= COST_TOL and ex <= X1_TOL and eu <= U0_TOL, (N, int(g["ticks"][k]), ec, ex, eu)
+
+
+@pytest.mark.parametrize("name,N", [("payload_N10", 10), ("perturbed_N20", 20), ("N60", 60)])
+def test_core_matches_round2_golden(golden, name, N):
+    """Payload variant (k1 = 7, masses 40.05 / 45 / 50), perturbed initial states (BASELINE config 3 recipe) and the long
+    horizon (config 5) against oracle-T (tests/golden/make_golden_r2.py)."""
+    g = golden[name]
+    for k in range(len(g["ticks"])):
+        r = hostsim.solve(problem(g, k, N))
+        assert r["status"] == 0, (name, int(g["ticks"][k]), r["status"])
+        assert r["viol"] <= VIOL_TOL
+        ec, ex, eu = golden_errors(g, k, r["cost"], r["X"][:20, 1], r["U"][:, 0])
+        assert ec <= COST_TOL and ex <= X1_TOL and eu <= U0_TOL, (name, int(g["ticks"][k]), ec, ex, eu)
 
 
 def test_analytic_stage_hessian_against_finite_differences(golden):
