@@ -12,6 +12,8 @@
  *   cmpc_get_trajectory    <- sol.value(self.opti_state) / sol.value(self.U) (:617, :630-631)
  *   cmpc_set_warm          <- opt.set_initial(U, ...), opt.set_initial(state, ...) (:630-631)
  *   cmpc_reset_warm        <- a fresh Opti (first tick is solved from the solver's default guess)
+ *   cmpc_assemble_device   <- the parameter assembly loops of `solve` (:482-600) + planner queries
+ *                             (footstep_planner_vertices.py:82-103), batched on the device
  *
  * Batch-first: B independent instances per call, one CTA per instance, all FP64.  Instance-major
  * layouts (each instance contiguous).  No torch types; plain pointers and sizes.  Every function
@@ -38,7 +40,8 @@ enum {
   CMPC_LINESEARCH = 2,
   CMPC_REGULARIZATION = 3,
   CMPC_INFEASIBLE_X0 = 4,   /* a row that depends on x0 only is violated (e.g. CoM z > 0.76, :230) */
-  CMPC_NAN = 5
+  CMPC_NAN = 5,
+  CMPC_STALL = 6            /* no progress within `stall_window` iterations at one barrier value (attempt abandoned) */
 };
 
 /* warm-start modes */
@@ -46,14 +49,18 @@ enum {
   CMPC_COLD = 0,          /* solver's own initial guess */
   CMPC_WARM_PRIMAL = 1,   /* states/inputs of the previous solve (what the reference does, :630-631) */
   CMPC_WARM_FULL = 2,     /* states, inputs, costates, slacks and multipliers of the previous solve */
-  CMPC_WARM_SHIFTED = 3   /* as FULL, moved one stage ahead first (consecutive ticks, mpc_rate * world_time_step = delta) */
+  CMPC_WARM_SHIFTED = 3,  /* as FULL, moved one stage ahead first (consecutive ticks, mpc_rate * world_time_step = delta) */
+  CMPC_WARM_AUTO = 4      /* per instance: SHIFTED while a landing (a foot's gamma going 0 -> 1) lies inside the horizon -- the
+                             switch moves one stage per tick --, FULL otherwise (references move 1.5 mm per tick) */
 };
 
 typedef struct cmpc_config {
   int32_t N;              /* horizon, params['N'] (:10) */
   int32_t max_iter;       /* interior-point iteration cap */
   int32_t ls_max;         /* backtracking steps of the filter line search */
-  int32_t threads;        /* threads per instance (CTA size), multiple of 32 */
+  int32_t threads;        /* threads per instance (CTA size): 128 */
+  int32_t stall_window;   /* an attempt whose barrier-problem error has not halved in this many iterations is abandoned (0 = off) */
+  int32_t reserved0;
   double delta;           /* world_time_step * mpc_rate (:11) */
   double grav;            /* params['g'] (:18) */
   double mu_fric;         /* 0.5 (:41) */
@@ -86,7 +93,11 @@ const char* cmpc_version(void);
  * Outputs (device): x1 [B][20] = state[:,1]; u0 [B][32] = U[:,0]; xN [B][20] = state[:,N];
  *   cost [B] (reference cost :311-351, without eps_reg term); viol [B] max unrelaxed violation of all
  *   rows and dynamics defects; status/iters [B].  Any output pointer may be NULL.
- * Asynchronous on `stream` (a cudaStream_t, may be NULL).  The warm-start state lives in the handle. */
+ * Asynchronous on `stream` (a cudaStream_t).  stream == NULL means the handle's own non-blocking stream, NOT the CUDA
+ * default stream.  Every operation on a handle is ordered after the previous operation on that handle, whatever streams
+ * the two were issued on (the handle records an event behind each operation and later operations wait for it).
+ * The warm-start state lives in the handle.  Instances that do not converge are solved again by up to three compact
+ * follow-up launches (cold start, other initial barrier values); `iters` accumulates over the attempts. */
 int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
                       const double* foot_ref, const double* gamma, const double* mass, const double* k1,
                       int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
@@ -98,6 +109,14 @@ int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const doubl
                     int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
                     int32_t* status, int32_t* iters);
 
+/* As cmpc_solve_host, and the full primal trajectories of the first `traj_batch` instances (X [traj_batch][N+1][20],
+ * U [traj_batch][N][32], host buffers) ride on the same device-to-host synchronisation: one call per control tick for the
+ * drop-in class (x1, u0 and `x_collect`, :614-617). */
+int cmpc_solve_host_traj(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
+                         const double* foot_ref, const double* gamma, const double* mass, const double* k1,
+                         int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
+                         int32_t* status, int32_t* iters, int32_t traj_batch, double* X, double* U);
+
 /* Full primal trajectories of the last solve to HOST buffers: X [B][N+1][20], U [B][N][32]. */
 int cmpc_get_trajectory(cmpc_handle* h, int32_t batch, double* X, double* U);
 /* Primal warm start from HOST buffers (same layouts); used with CMPC_WARM_PRIMAL. */
@@ -107,8 +126,9 @@ int cmpc_set_warm(cmpc_handle* h, int32_t batch, const double* X, const double* 
  * what-if sweeps from one nominal solution).  Restore is asynchronous on `stream` (may be NULL). */
 int cmpc_warm_save(cmpc_handle* h, int32_t batch);
 int cmpc_warm_restore(cmpc_handle* h, int32_t batch, void* stream);
-/* Forget the warm-start state of all instances. */
-int cmpc_reset_warm(cmpc_handle* h);
+/* Forget the warm-start state: of all instances (mask == NULL) or of the instances b < n with mask[b] != 0 (host buffer).
+ * A warm solve of an instance without warm-start state starts cold. */
+int cmpc_reset_warm(cmpc_handle* h, const uint8_t* mask, int32_t n);
 /* Sum over the last batch of (interior-point iterations, Riccati factorisations, regularisation retries),
  * device time of the last solve kernel in milliseconds (CUDA events) and kernels launched by it. */
 int cmpc_last_stats(cmpc_handle* h, int64_t* iters, int64_t* nfact, int64_t* nreg, double* kernel_ms,
@@ -117,8 +137,34 @@ int cmpc_last_stats(cmpc_handle* h, int64_t* iters, int64_t* nfact, int64_t* nre
  * 11 values: eval, assemble, P[B A] products, factorisation, factor store, forward sweep, slack steps, trials, step,
  * whole solves, CTA lifetimes. */
 int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out11);
-/* Bytes of device workspace per instance and shared memory per CTA. */
-int cmpc_footprint(const cmpc_handle* h, size_t* work_bytes_per_instance, size_t* smem_bytes_per_cta);
+/* Device memory: bytes of iterate per instance (resident across ticks), bytes of scratch per resident CTA slot (Newton
+ * step, derivative records, stage factors of the solve the slot is running), number of slots, shared memory per CTA. */
+int cmpc_footprint(const cmpc_handle* h, size_t* iterate_bytes_per_instance, size_t* scratch_bytes_per_slot, int32_t* slots,
+                   size_t* smem_bytes_per_cta);
+
+/* ---- batched per-tick parameter assembly on the device ------------------------------------------
+ * Tables of one walk, device pointers, built once by the caller from the planner / reference generator outputs:
+ *   com_tab    [T_ref][9]   CoM_ref pos/vel/acc x,y,z per absolute tick (MPC file :64-74), cut to the shortest table
+ *   foot_tab   [T_ref][8]   position_contacts_ref: p_l(3), p_r(3), yaw_l, yaw_r (:77-84)
+ *   gamma_tab  [T_plan][2]  contact schedule per absolute tick from get_phase_at_time / plan[..]['foot_id'] (:515-534)
+ *   step_index [T_plan]     get_step_index_at_time (footstep_planner_vertices.py:82-88) */
+typedef struct cmpc_walk_tables {
+  int32_t N, rate, first_swing_left, n_steps, T_ref, T_plan;
+  const double* com_tab;
+  const double* foot_tab;
+  const double* gamma_tab;
+  const int32_t* step_index;
+} cmpc_walk_tables;
+
+/* x0 / com_ref / foot_ref / gamma of `batch` robots (layouts of cmpc_solve_device), robot b at its own tick[b]: replaces
+ * the O(N * steps) Python loops and 4N set_value calls of `solve` (:482-600).  Per robot inputs (device): measured CoM
+ * position / velocity / angular momentum [B][3], theta_hat of the previous solution [B][3] (:485), measured foot yaws
+ * [B][2], the robot's (step-adjusted) plan positions [B][n_steps][3].  err[b] (may be NULL): 0 ok, 1 the horizon runs
+ * past the reference tables (the reference's IndexError, :567), 2 past the footstep plan; such robots are not written.
+ * One gather kernel on `stream` (NULL = default stream) of GPU `device`. */
+int cmpc_assemble_device(const cmpc_walk_tables* tb, int32_t device, int32_t batch, const int32_t* tick, const double* com_pos,
+                         const double* com_vel, const double* hw, const double* theta, const double* yaw, const double* plan,
+                         double* x0, double* com_ref, double* foot_ref, double* gamma, int32_t* err, void* stream);
 
 /* Peak-FP64 probe: runs a dependent-free DFMA loop on every SM and returns the measured TFLOP/s. */
 int cmpc_measure_fp64_peak(int32_t device, double* tflops);

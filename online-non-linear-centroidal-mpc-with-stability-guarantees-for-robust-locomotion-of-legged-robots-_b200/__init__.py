@@ -13,12 +13,12 @@ Layout
 
 There is no CPU path: creating a solver without the CUDA library or without a GPU raises.
 """
-from ._lib import BatchSolver, CmpcError, build_library, library_path, measure_fp64_peak  # noqa: F401
+from ._lib import BatchSolver, CmpcError, WalkTables, build_library, library_path, measure_fp64_peak  # noqa: F401
 from .assembly import PlanTables, assemble_tick, pack_instances  # noqa: F401
 from .parallel import gather_stats, shard_arrays, shard_range  # noqa: F401
 from .fleet import Fleet  # noqa: F401
 from .com_reference import quintic_coefficients, references_from_knots, sample_tables  # noqa: F401
 
-__all__ = ["BatchSolver", "CmpcError", "build_library", "library_path", "measure_fp64_peak",
+__all__ = ["BatchSolver", "CmpcError", "WalkTables", "build_library", "library_path", "measure_fp64_peak",
            "PlanTables", "assemble_tick", "pack_instances", "gather_stats", "shard_arrays", "shard_range", "Fleet",
            "quintic_coefficients", "references_from_knots", "sample_tables"]

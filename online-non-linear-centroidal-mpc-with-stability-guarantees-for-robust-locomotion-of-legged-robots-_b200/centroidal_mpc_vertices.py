@@ -4,15 +4,15 @@
   reference                                   here
   cs.Opti() + NLP build (:126-353)            BatchSolver(N, 1) -> cmpc_create
   opt.set_value(...) x (4N + 4) (:511-600)    assembly.assemble_tick (table look-ups)
-  opt.solve() (:606)                          cmpc_solve_host (H2D, one kernel, D2H)
-  sol.value(...) (:614-619)                   x1 / u0 outputs + cmpc_get_trajectory
+  opt.solve() (:606)                          cmpc_solve_host_traj (H2D, solve, D2H of x1 / u0 and the trajectories:
+  sol.value(...) (:614-619)                   one call and one synchronisation per control tick)
   opt.set_initial(...) (:630-631)             warm-start state stays on the device inside the handle
 """
 from __future__ import annotations
 
 import numpy as np
 
-from ._lib import COLD, WARM_FULL, WARM_PRIMAL, BatchSolver, STATUS_NAMES
+from ._lib import COLD, WARM_AUTO, WARM_FULL, WARM_PRIMAL, BatchSolver, STATUS_NAMES  # noqa: F401
 from .assembly import PlanTables, ReferenceTables, assemble_tick
 
 _K1_DEFAULT = (4.0, 0.1)      # (:27-28)
@@ -23,7 +23,7 @@ class centroidal_mpc:  # noqa: N801  (reference class name)
     K1K2 = None               # the payload module overrides this with (7, 1)
 
     def __init__(self, initial, footstep_planner, params, CoM_ref, contact_trj_l=None, contact_trj_r=None,
-                 device=0, warm_mode=WARM_FULL, **solver_overrides):
+                 device=0, warm_mode=WARM_AUTO, **solver_overrides):
         self.params = params
         self.N = params["N"]
         self.delta = params["world_time_step"] * params["mpc_rate"]
@@ -67,12 +67,12 @@ class centroidal_mpc:  # noqa: N801  (reference class name)
                                              self.model_state["theta_hat"]["val"], t)
         self.current_state = x0
         mode = COLD if self._first else self._warm_mode
-        out = self._solver.solve_host(x0[None], com[None], foot[None], gamma[None], self.mass, self.k1, mode)
+        out = self._solver.solve_host(x0[None], com[None], foot[None], gamma[None], self.mass, self.k1, mode, traj_batch=1)
         self._first = False
         self.last_status, self.last_iters, self.last_cost = int(out["status"][0]), int(out["iters"][0]), float(out["cost"][0])
         if self.last_status != 0:                                  # the reference dies here (:605-614)
             raise RuntimeError("centroidal MPC solve failed at t=%d: %s" % (t, STATUS_NAMES.get(self.last_status)))
-        X, U = self._solver.trajectory(1)
+        X, U = out["X"], out["U"]                               # same device-to-host synchronisation as x1 / u0
         self.x = out["x1"][0].copy()                               # :614
         self.u = out["u0"][0].copy()                               # :616
         self.x_collect = X[0].T.copy()                             # :617  (20, N+1)

@@ -46,6 +46,24 @@ struct ParCta {
   __device__ int nwarps() const { return (int)(blockDim.x >> 5); }
   __device__ int lanes() const { return 32; }
   __device__ void sync_warp() const { __syncwarp(); }
+  __device__ bool sync_and(bool p) const { return __syncthreads_and(p ? 1 : 0) != 0; }     // barrier + block vote
+  __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }            // warp vote
+  // warp all-reduce by xor shuffles (every lane ends with the result)
+  __device__ double wmax(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+  }
+  __device__ double wmin(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+  }
+  __device__ double wsum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
   // asynchronous global -> shared copy of n doubles, spread over the CTA (cp.async, 8 bytes per element)
   __device__ void copy_async(double* dst, const double* src, int n) const {
     for (int t = (int)threadIdx.x; t < n; t += (int)blockDim.x) {
@@ -66,19 +84,34 @@ struct Outputs {
   unsigned long long* prof;   // [PF_COUNT] phase cycles summed over CTAs (only with -DCMPC_PROFILE)
 };
 
+// One launch = one PASS over a list of instances.  Persistent CTAs (one per resident slot: SMs x CTAs per SM) pull
+// instances from an atomic work counter in list order; the scratch (Newton step, derivative records, stage factors)
+// belongs to the CTA slot, only the iterate belongs to the instance.  Pass 0 solves every instance as asked (warm or
+// cold); an instance that does not converge is appended to `list_out` and solved again by the next pass from the
+// solver's own cold start with another initial barrier value (mu_scale) -- a second, compact launch over the failed
+// subset instead of a retry loop inside the CTA, which left every other slot waiting for the few long ones.
 __global__ void __launch_bounds__(CMPC_THREADS, CMPC_MIN_CTAS)
 cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const double* __restrict__ com_ref,
                   const double* __restrict__ foot_ref, const double* __restrict__ gamma,
-                  const double* __restrict__ mass, const double* __restrict__ k1, double* work, size_t wstride,
-                  int warm, Outputs out, const int32_t* __restrict__ perm, int32_t* __restrict__ last_iters) {
+                  const double* __restrict__ mass, const double* __restrict__ k1, double* iter, size_t istride,
+                  double* scratch, size_t sstride, int warm, double mu_scale, int accumulate, Outputs out,
+                  const int32_t* __restrict__ list_in, const int32_t* __restrict__ count_in, int32_t* __restrict__ list_out,
+                  int32_t* count_out, int32_t* next, int32_t* __restrict__ last_iters, int32_t* __restrict__ valid) {
   Smem& sm = *reinterpret_cast<Smem*>(cmpc_smem_raw);
   const int N = c.N;
+  const int n = count_in ? *count_in : batch;
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0) for (int k = 0; k < PF_COUNT; ++k) sm.prof[k] = 0;
   const long long cta_t0 = clock64();
 #endif
-  for (int slot = blockIdx.x; slot < batch; slot += gridDim.x) {
-    const int b = perm ? perm[slot] : slot;          // longest-expected-first order (see cmpc_order_kernel)
+  double* my_scratch = scratch + sstride * blockIdx.x;
+  for (;;) {
+    if (threadIdx.x == 0) sm.flag = atomicAdd(next, 1);
+    __syncthreads();
+    const int slot = sm.flag;
+    __syncthreads();
+    if (slot >= n) break;
+    const int b = list_in ? list_in[slot] : slot;    // pass 0: longest-expected-first order (cmpc_order_kernel); retries: the failed subset
     Instance in;
     in.x0 = x0 + (size_t)NXP * b;
     in.com_ref = com_ref + (size_t)9 * N * b;
@@ -86,14 +119,15 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
     in.gamma = gamma + (size_t)2 * (N + 1) * b;
     in.mass = mass[b];
     in.k1 = k1[b];
-    Work w = carve_work(work + wstride * b, N);
+    Work w = carve_work(iter + istride * b, my_scratch, N);
+    const int wm = (warm != 0 && valid && !valid[b]) ? 0 : warm;      // no previous solution of this instance: cold
     ParCta par;
     Solver<ParCta> sol(c, in, w, sm, par);
     Stats st;
 #ifdef CMPC_PROFILE
     const long long solve_t0 = clock64();
 #endif
-    sol.run(warm, &st);
+    sol.run_pass(wm, mu_scale, &st);
     __syncthreads();
 #ifdef CMPC_PROFILE
     if (threadIdx.x == 0) sm.prof[PF_SOLVE] += clock64() - solve_t0;
@@ -106,9 +140,14 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
       if (out.cost) out.cost[b] = st.cost;
       if (out.viol) out.viol[b] = st.viol;
       if (out.status) out.status[b] = st.status;
-      if (out.iters) out.iters[b] = st.iters;
-      if (out.counters) { out.counters[2 * b] = st.nfact; out.counters[2 * b + 1] = st.nreg; }
-      if (last_iters) last_iters[b] = st.nfact;
+      if (out.iters) out.iters[b] = (accumulate ? out.iters[b] : 0) + st.iters;
+      if (out.counters) {
+        out.counters[2 * b] = (accumulate ? out.counters[2 * b] : 0) + st.nfact;
+        out.counters[2 * b + 1] = (accumulate ? out.counters[2 * b + 1] : 0) + st.nreg;
+      }
+      if (last_iters) last_iters[b] = (accumulate ? last_iters[b] : 0) + st.nfact;
+      if (valid) valid[b] = 1;
+      if (list_out && st.status != ST_CONVERGED && st.status != ST_INFEASIBLE_X0) list_out[atomicAdd(count_out, 1)] = b;
     }
     __syncthreads();
   }
@@ -145,18 +184,19 @@ __global__ void cmpc_order_kernel(int batch, int N, const int32_t* __restrict__ 
 }
 
 // gather / scatter between the 28-wide internal state layout and the 20-wide reference layout
-__global__ void cmpc_export_traj(int batch, int N, const double* work, size_t wstride, double* X, double* U) {
+__global__ void cmpc_export_traj(int batch, int N, const double* iter, size_t istride, double* X, double* U) {
   const int b = blockIdx.x;
   if (b >= batch) return;
-  Work w = carve_work(const_cast<double*>(work) + wstride * b, N);
+  Work w = carve_work(const_cast<double*>(iter) + istride * b, nullptr, N);
   for (int t = threadIdx.x; t < (N + 1) * NXP; t += blockDim.x) X[(size_t)b * (N + 1) * NXP + t] = w.X[(t / NXP) * NX + t % NXP];
   for (int t = threadIdx.x; t < N * NU; t += blockDim.x) U[(size_t)b * N * NU + t] = w.U[t];
 }
 
-__global__ void cmpc_import_traj(int batch, int N, double* work, size_t wstride, const double* X, const double* U) {
+__global__ void cmpc_import_traj(int batch, int N, double* iter, size_t istride, const double* X, const double* U, int32_t* valid) {
   const int b = blockIdx.x;
   if (b >= batch) return;
-  Work w = carve_work(work + wstride * b, N);
+  if (threadIdx.x == 0 && valid) valid[b] = 1;
+  Work w = carve_work(iter + istride * b, nullptr, N);
   for (int t = threadIdx.x; t < (N + 1) * NXP; t += blockDim.x) w.X[(t / NXP) * NX + t % NXP] = X[(size_t)b * (N + 1) * NXP + t];
   for (int t = threadIdx.x; t < N * NU; t += blockDim.x) w.U[t] = U[(size_t)b * N * NU + t];
   __syncthreads();
@@ -165,6 +205,60 @@ __global__ void cmpc_import_traj(int batch, int N, double* work, size_t wstride,
     const int i = t / NQ, v = t % NQ;
     w.X[i * NX + IQ + v] = (i >= 1) ? w.U[(i - 1) * NU + 3 * v + 2] : 0.0;
   }
+}
+
+// Per-tick parameter assembly of `centroidal_mpc.solve` (MPC file :482-600) for a batch of robots, each at its own tick:
+// one CTA per robot gathers its x0, CoM / foot references, yaw references (with the column-major quirk of :599-600) and
+// contact schedule from the walk's tables.  Pure gather: 8 (19 N + 22) bytes written per robot, coalesced per section.
+__global__ void cmpc_assemble_kernel(cmpc_walk_tables tb, int batch, const int32_t* __restrict__ tick, const double* __restrict__ com_pos,
+                                     const double* __restrict__ com_vel, const double* __restrict__ hw, const double* __restrict__ theta,
+                                     const double* __restrict__ yaw, const double* __restrict__ plan, double* __restrict__ x0,
+                                     double* __restrict__ com_ref, double* __restrict__ foot_ref, double* __restrict__ gamma, int32_t* __restrict__ err) {
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  const int N = tb.N, rate = tb.rate, t = tick[b];
+  int e = 0;
+  if (t < 0 || t + N * rate >= tb.T_ref) e = 1;                 // the reference's IndexError (:567)
+  else if (t + N * rate >= tb.T_plan) e = 2;                   // beyond the footstep plan (get_step_index_at_time returns None)
+  if (threadIdx.x == 0 && err) err[b] = e;
+  if (e) return;
+  for (int j = threadIdx.x; j < NXP; j += blockDim.x) {
+    double v;
+    if (j < 3) v = com_pos[3 * b + j];
+    else if (j < 6) v = com_vel[3 * b + j - 3];
+    else if (j < 9) v = hw[3 * b + j - 6];
+    else if (j < 12) v = theta[3 * b + j - 9];
+    else if (j == IPSL) v = yaw[2 * b];
+    else if (j == IPSR) v = yaw[2 * b + 1];
+    else {
+      const int right = j >= IPR, ax = j - (right ? IPR : IPL);
+      if (t < 200) v = tb.foot_tab[(size_t)8 * t + 3 * right + ax];                                  // :493-495
+      else {                                                                                         // :496-503
+        const int index = tb.step_index[t - 70];
+        const int a_ = index + (index % 2), b_ = index + (((index - 1) % 2 + 2) % 2);
+        const int il = tb.first_swing_left ? a_ : b_, ir = tb.first_swing_left ? b_ : a_;
+        v = plan[((size_t)b * tb.n_steps + (right ? ir : il)) * 3 + ax];
+      }
+    }
+    x0[(size_t)NXP * b + j] = v;
+  }
+  for (int q = threadIdx.x; q < N * 9; q += blockDim.x) {
+    const int i = q / 9, j = q - 9 * i;
+    com_ref[(size_t)9 * N * b + q] = tb.com_tab[(size_t)9 * (t + (1 + i) * rate) + j];              // :565-575
+  }
+  for (int q = threadIdx.x; q < N * 8; q += blockDim.x) {
+    const int i = q >> 3, j = q & 7;
+    const int tt = (j < 6) ? t + (1 + i) * rate : t + (1 + i / 3) * rate;                             // yaw: column-major quirk (:599-600)
+    foot_ref[(size_t)8 * N * b + q] = tb.foot_tab[(size_t)8 * tt + j];
+  }
+  for (int q = threadIdx.x; q < 2 * (N + 1); q += blockDim.x)
+    gamma[(size_t)2 * (N + 1) * b + q] = tb.gamma_tab[(size_t)2 * (t + (q >> 1) * rate) + (q & 1)];  // :517-531
+}
+
+// forget the warm-start state of the flagged instances
+__global__ void cmpc_clear_valid(int n, const uint8_t* __restrict__ mask, int32_t* __restrict__ valid) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n && (!mask || mask[b])) valid[b] = 0;
 }
 
 __global__ void cmpc_fp64_probe(double* out, int iters) {
@@ -182,34 +276,66 @@ __global__ void cmpc_fp64_probe(double* out, int iters) {
 struct cmpc_handle {
   Config cfg;
   int threads, cap, device;
-  size_t wstride;            // doubles per instance
-  double* work;
+  int slots;                 // resident CTA slots of the solve kernel on this GPU (SMs x CTAs per SM)
+  size_t istride, sstride;   // doubles: iterate per instance, scratch per slot
+  double* iter;              // [cap][istride]   device resident across ticks (warm starts)
+  double* scratch;           // [slots][sstride] Newton step, derivative records, stage factors of the running solves
   // device staging for the host-buffer entry point
   double* d_in; double* d_out; int32_t* d_iout;
   double* h_in; double* h_out; int32_t* h_iout;
   int32_t* d_counters; int32_t* h_counters;
   int32_t* d_last_iters; int32_t* d_perm;     // work of the previous solve per instance, launch order of the next one
+  int32_t* d_valid;                           // per instance: a previous solution exists (warm start possible)
+  int32_t* d_queue;                           // [0..3] work counters of the passes, [4..7] lengths of the retry lists
+  int32_t* d_fail;                            // [3][cap] instances to retry
+  uint8_t* d_mask;                            // staging of cmpc_reset_warm's mask
+  double* d_traj; double* h_traj; size_t traj_cap;   // trajectory staging (allocated at first use, kept)
   unsigned long long* d_prof;
-  size_t in_doubles, out_doubles;
-  cudaStream_t stream;
+  size_t in_doubles, out_doubles, traj_doubles;
+  cudaStream_t stream;       // the handle's own stream (used when the caller passes stream == NULL)
+  cudaStream_t last_stream;  // stream of the last operation on this handle ...
+  cudaEvent_t ev_done;       // ... and the event recorded behind it: operations on another stream wait for it
+  bool have_done;
   cudaEvent_t ev0, ev1;
   int last_batch, last_launches;
   size_t smem_bytes;         // dynamic shared memory per CTA (sizeof(Smem) + the occupancy-probe padding CMPC_SMEM_PAD)
   bool have_timing;
-  int warm_valid;
-  double* snap; int32_t* snap_iters; int snap_batch; size_t iter_doubles;   // snapshot of the warm-start part of the workspace
+  double* snap; int32_t* snap_iters; int32_t* snap_valid; int snap_batch;   // snapshot of the warm-start state
 };
+
+namespace {
+
+// Every operation on a handle is ordered after the previous one, whatever streams the two were issued on.
+int order_after_last(cmpc_handle* h, cudaStream_t s) {
+  if (h->have_done && h->last_stream != s) CK(cudaStreamWaitEvent(s, h->ev_done, 0), "cudaStreamWaitEvent");
+  return 0;
+}
+int mark_done(cmpc_handle* h, cudaStream_t s) {
+  CK(cudaEventRecord(h->ev_done, s), "cudaEventRecord");
+  h->last_stream = s; h->have_done = true;
+  return 0;
+}
+
+int ensure_traj(cmpc_handle* h) {
+  if (h->d_traj) return 0;
+  const size_t n = (size_t)h->cap * h->traj_doubles;
+  CK(cudaMalloc(&h->d_traj, n * sizeof(double)), "cudaMalloc(trajectory staging)");
+  CK(cudaMallocHost(&h->h_traj, n * sizeof(double)), "cudaMallocHost(trajectory staging)");
+  return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
 const char* cmpc_last_error(void) { return g_err; }
-const char* cmpc_version(void) { return "cmpc_b200 0.1 (sm_100a, fp64)"; }
+const char* cmpc_version(void) { return "cmpc_b200 0.2 (sm_100a, fp64)"; }
 
 int cmpc_default_config(int32_t N, cmpc_config* cfg) {
   if (!cfg || N < 1 || N > NMAX) return fail(-1, "cmpc_default_config: bad arguments (1 <= N <= 64)");
   Config c = default_config(N);
   memset(cfg, 0, sizeof(*cfg));
-  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS;
+  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS; cfg->stall_window = c.stall_window;
   cfg->delta = c.delta; cfg->grav = c.grav; cfg->mu_fric = c.mu_fric;
   cfg->foot_half_len = c.hl; cfg->foot_half_wid = c.hw;
   cfg->w_h = c.w_h; cfg->w_xy = c.w_xy; cfg->w_zc = c.w_zc; cfg->w_foot = c.w_foot; cfg->w_sym = c.w_sym;
@@ -223,7 +349,8 @@ int cmpc_default_config(int32_t N, cmpc_config* cfg) {
 
 static Config to_internal(const cmpc_config* u) {
   Config c = default_config(u->N);
-  c.max_iter = u->max_iter; c.ls_max = u->ls_max; c.delta = u->delta; c.grav = u->grav; c.mu_fric = u->mu_fric;
+  c.max_iter = u->max_iter; c.ls_max = u->ls_max; c.stall_window = u->stall_window;
+  c.delta = u->delta; c.grav = u->grav; c.mu_fric = u->mu_fric;
   c.hl = u->foot_half_len; c.hw = u->foot_half_wid; c.w_h = u->w_h; c.w_xy = u->w_xy; c.w_zc = u->w_zc;
   c.w_foot = u->w_foot; c.w_sym = u->w_sym; c.w_swing = u->w_swing; c.w_rate = u->w_rate; c.eps_reg = u->eps_reg;
   c.pz_max = u->pz_max; for (int j = 0; j < 3; ++j) c.box[j] = u->box[j];
@@ -247,38 +374,62 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
   memset(h, 0, sizeof(*h));
   h->cfg = to_internal(cfg); h->threads = cfg->threads; h->cap = batch_capacity; h->device = device;
   const int N = cfg->N;
-  h->wstride = (work_doubles(N) + 1) & ~(size_t)1;       // keep instances 16-byte aligned
+  h->istride = (iter_doubles(N) + 1) & ~(size_t)1;       // keep blocks 16-byte aligned
+  h->sstride = (scratch_doubles(N) + 1) & ~(size_t)1;
   h->in_doubles = (size_t)NXP + 9 * N + 8 * N + 2 * (N + 1) + 2;
   h->out_doubles = (size_t)NXP + NU + NXP + 2;
+  h->traj_doubles = (size_t)(N + 1) * NXP + (size_t)N * NU;
   const size_t B = (size_t)batch_capacity;
-  CK(cudaMalloc(&h->work, B * h->wstride * sizeof(double)), "cudaMalloc(work)");
-  CK(cudaMemset(h->work, 0, B * h->wstride * sizeof(double)), "cudaMemset(work)");
-  CK(cudaMalloc(&h->d_in, B * h->in_doubles * sizeof(double)), "cudaMalloc(d_in)");
-  CK(cudaMalloc(&h->d_out, B * h->out_doubles * sizeof(double)), "cudaMalloc(d_out)");
-  CK(cudaMalloc(&h->d_iout, B * 2 * sizeof(int32_t)), "cudaMalloc(d_iout)");
-  CK(cudaMalloc(&h->d_counters, B * 2 * sizeof(int32_t)), "cudaMalloc(d_counters)");
-  CK(cudaMalloc(&h->d_last_iters, B * sizeof(int32_t)), "cudaMalloc(d_last_iters)");
-  CK(cudaMemset(h->d_last_iters, 0, B * sizeof(int32_t)), "cudaMemset(d_last_iters)");
-  CK(cudaMalloc(&h->d_perm, B * sizeof(int32_t)), "cudaMalloc(d_perm)");
-  CK(cudaMallocHost(&h->h_in, B * h->in_doubles * sizeof(double)), "cudaMallocHost(h_in)");
-  CK(cudaMallocHost(&h->h_out, B * h->out_doubles * sizeof(double)), "cudaMallocHost(h_out)");
-  CK(cudaMallocHost(&h->h_iout, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_iout)");
-  CK(cudaMallocHost(&h->h_counters, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_counters)");
-#ifdef CMPC_PROFILE
-  CK(cudaMalloc(&h->d_prof, PF_COUNT * sizeof(unsigned long long)), "cudaMalloc(d_prof)");
-#endif
-  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  CK(cudaEventCreate(&h->ev0), "cudaEventCreate");
-  CK(cudaEventCreate(&h->ev1), "cudaEventCreate");
+  int rc = 0;
+  // (every failure below releases what has been allocated so far)
+#define CKC(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(-2, what, e_); cmpc_destroy(h); return rc; } } while (0)
   h->smem_bytes = sizeof(Smem);
   if (const char* pad = getenv("CMPC_SMEM_PAD")) h->smem_bytes += (size_t)atol(pad);     // profiling aid: fewer resident CTAs per SM
-  CK(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes),
-     "cudaFuncSetAttribute(smem)");
+  CKC(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes),
+      "cudaFuncSetAttribute(smem)");
 #if CMPC_MIN_CTAS >= 4
   // more than three resident CTAs per SM need a shared-memory carve-out beyond the driver's default choice
-  CK(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared),
-     "cudaFuncSetAttribute(carveout)");
+  CKC(cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared),
+      "cudaFuncSetAttribute(carveout)");
 #endif
+  {
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    int per_sm = 0;
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmpc_solve_kernel, h->threads, h->smem_bytes), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) per_sm = 1;
+    h->slots = per_sm * prop.multiProcessorCount;
+    if (const char* sl = getenv("CMPC_SLOTS")) { const int v = atoi(sl); if (v > 0) h->slots = v; }          // experiments
+  }
+  const size_t nslots = (size_t)(h->slots < batch_capacity ? h->slots : batch_capacity);
+  CKC(cudaMalloc(&h->iter, B * h->istride * sizeof(double)), "cudaMalloc(iterates)");
+  CKC(cudaMemset(h->iter, 0, B * h->istride * sizeof(double)), "cudaMemset(iterates)");
+  CKC(cudaMalloc(&h->scratch, nslots * h->sstride * sizeof(double)), "cudaMalloc(scratch)");
+  CKC(cudaMemset(h->scratch, 0, nslots * h->sstride * sizeof(double)), "cudaMemset(scratch)");
+  CKC(cudaMalloc(&h->d_in, B * h->in_doubles * sizeof(double)), "cudaMalloc(d_in)");
+  CKC(cudaMalloc(&h->d_out, B * h->out_doubles * sizeof(double)), "cudaMalloc(d_out)");
+  CKC(cudaMalloc(&h->d_iout, B * 2 * sizeof(int32_t)), "cudaMalloc(d_iout)");
+  CKC(cudaMalloc(&h->d_counters, B * 2 * sizeof(int32_t)), "cudaMalloc(d_counters)");
+  CKC(cudaMalloc(&h->d_last_iters, B * sizeof(int32_t)), "cudaMalloc(d_last_iters)");
+  CKC(cudaMemset(h->d_last_iters, 0, B * sizeof(int32_t)), "cudaMemset(d_last_iters)");
+  CKC(cudaMalloc(&h->d_perm, B * sizeof(int32_t)), "cudaMalloc(d_perm)");
+  CKC(cudaMalloc(&h->d_valid, B * sizeof(int32_t)), "cudaMalloc(d_valid)");
+  CKC(cudaMemset(h->d_valid, 0, B * sizeof(int32_t)), "cudaMemset(d_valid)");
+  CKC(cudaMalloc(&h->d_queue, 8 * sizeof(int32_t)), "cudaMalloc(d_queue)");
+  CKC(cudaMalloc(&h->d_fail, 3 * B * sizeof(int32_t)), "cudaMalloc(d_fail)");
+  CKC(cudaMalloc(&h->d_mask, B), "cudaMalloc(d_mask)");
+  CKC(cudaMallocHost(&h->h_in, B * h->in_doubles * sizeof(double)), "cudaMallocHost(h_in)");
+  CKC(cudaMallocHost(&h->h_out, B * h->out_doubles * sizeof(double)), "cudaMallocHost(h_out)");
+  CKC(cudaMallocHost(&h->h_iout, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_iout)");
+  CKC(cudaMallocHost(&h->h_counters, B * 2 * sizeof(int32_t)), "cudaMallocHost(h_counters)");
+#ifdef CMPC_PROFILE
+  CKC(cudaMalloc(&h->d_prof, PF_COUNT * sizeof(unsigned long long)), "cudaMalloc(d_prof)");
+#endif
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  CKC(cudaEventCreate(&h->ev0), "cudaEventCreate");
+  CKC(cudaEventCreate(&h->ev1), "cudaEventCreate");
+  CKC(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming), "cudaEventCreate");
+#undef CKC
   *out = h;
   return 0;
 }
@@ -286,12 +437,52 @@ int cmpc_create(const cmpc_config* cfg, int32_t batch_capacity, int32_t device, 
 int cmpc_destroy(cmpc_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaFree(h->snap); cudaFree(h->snap_iters); cudaFree(h->work); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_iout); cudaFree(h->d_counters); cudaFree(h->d_last_iters); cudaFree(h->d_perm);
-  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_iout); cudaFreeHost(h->h_counters);
+  cudaDeviceSynchronize();
+  cudaFree(h->snap); cudaFree(h->snap_iters); cudaFree(h->snap_valid); cudaFree(h->iter); cudaFree(h->scratch); cudaFree(h->d_in); cudaFree(h->d_out);
+  cudaFree(h->d_iout); cudaFree(h->d_counters); cudaFree(h->d_last_iters); cudaFree(h->d_perm); cudaFree(h->d_valid); cudaFree(h->d_queue);
+  cudaFree(h->d_fail); cudaFree(h->d_mask); cudaFree(h->d_traj); cudaFree(h->d_prof);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_iout); cudaFreeHost(h->h_counters); cudaFreeHost(h->h_traj);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   delete h;
+  return 0;
+}
+
+// the launches of one solve on stream s (no ordering / bookkeeping)
+static int launch_solve(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref, const double* foot_ref, const double* gamma,
+                        const double* mass, const double* k1, int32_t warm_mode, const Outputs& o, cudaStream_t s, int* launches) {
+  const size_t B = (size_t)h->cap;
+  CK(cudaMemsetAsync(h->d_queue, 0, 8 * sizeof(int32_t), s), "memset queue");
+  const int32_t* list = nullptr;
+  int nl = 0;
+  if (warm_mode != CMPC_COLD) {                       // the previous solve of these instances tells how expensive they are
+    cmpc_order_kernel<<<1, 1024, 0, s>>>(batch, h->cfg.N, h->d_last_iters, gamma, h->d_perm);
+    CK(cudaGetLastError(), "cmpc_order_kernel launch");
+    list = h->d_perm; ++nl;
+  }
+  const int grid = batch < h->slots ? batch : h->slots;
+  // pass 0: as asked.  Retries (compact launches over the failed subset, usually empty: their CTAs exit at once): from
+  // the solver's cold start with initial barrier x 1 (only after a warm attempt), x 10, x 0.1
+  const double scale[4] = {1.0, 1.0, 10.0, 0.1};
+  int prev = -1;                                      // index of the fail list the previous pass wrote
+  for (int p = 0; p < 4; ++p) {
+    if (p == 1 && warm_mode == CMPC_COLD) continue;   // a cold attempt with the same barrier value would repeat pass 0
+    const bool last = (p == 3);
+    const int32_t* lin = (p == 0) ? list : h->d_fail + (size_t)prev * B;
+    const int32_t* cin = (p == 0) ? nullptr : h->d_queue + 4 + p;
+    int32_t* lout = last ? nullptr : h->d_fail + (size_t)(prev + 1) * B;
+    // the next LAUNCHED pass reads its count from d_queue[4 + its index]
+    const int pnext = (p == 0 && warm_mode == CMPC_COLD) ? 2 : p + 1;
+    int32_t* cout = last ? nullptr : h->d_queue + 4 + pnext;
+    cmpc_solve_kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1, h->iter, h->istride,
+                                                              h->scratch, h->sstride, p == 0 ? warm_mode : CMPC_COLD, scale[p], p > 0, o, lin, cin, lout, cout,
+                                                              h->d_queue + p, h->d_last_iters, h->d_valid);
+    CK(cudaGetLastError(), "cmpc_solve_kernel launch");
+    ++nl; ++prev;
+  }
+  *launches = nl;
   return 0;
 }
 
@@ -302,42 +493,37 @@ int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const dou
   if (!h) return fail(-1, "cmpc_solve_device: null handle");
   if (batch < 1 || batch > h->cap) return fail(-1, "cmpc_solve_device: batch exceeds the handle's capacity");
   if (!x0 || !com_ref || !foot_ref || !gamma || !mass || !k1) return fail(-1, "cmpc_solve_device: null input pointer");
-  if (warm_mode < 0 || warm_mode > 3) return fail(-1, "cmpc_solve_device: bad warm_mode");
-  if (warm_mode != CMPC_COLD && h->warm_valid < batch) warm_mode = CMPC_COLD;     // nothing to warm-start from
+  if (warm_mode < 0 || warm_mode > 4) return fail(-1, "cmpc_solve_device: bad warm_mode");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  if (int rc = order_after_last(h, s)) return rc;
   Outputs o{x1, u0, xN, cost, viol, status, iters, h->d_counters, h->d_prof};
   if (h->d_prof) CK(cudaMemsetAsync(h->d_prof, 0, PF_COUNT * sizeof(unsigned long long), s), "memset prof");
   CK(cudaEventRecord(h->ev0, s), "cudaEventRecord");
-  const int32_t* perm = nullptr;
-  int launches = 1;
-  if (warm_mode != CMPC_COLD) {                       // the previous solve of these instances tells how expensive they are
-    cmpc_order_kernel<<<1, 1024, 0, s>>>(batch, h->cfg.N, h->d_last_iters, gamma, h->d_perm);
-    CK(cudaGetLastError(), "cmpc_order_kernel launch");
-    perm = h->d_perm; launches = 2;
-  }
-  cmpc_solve_kernel<<<batch, h->threads, h->smem_bytes, s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1,
-                                                            h->work, h->wstride, warm_mode, o, perm, h->d_last_iters);
-  CK(cudaGetLastError(), "cmpc_solve_kernel launch");
+  int launches = 0;
+  if (int rc = launch_solve(h, batch, x0, com_ref, foot_ref, gamma, mass, k1, warm_mode, o, s, &launches)) return rc;
   CK(cudaEventRecord(h->ev1, s), "cudaEventRecord");
   h->last_batch = batch; h->last_launches = launches; h->have_timing = true;
-  h->warm_valid = batch;
-  return 0;
+  return mark_done(h, s);
 }
 
-int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
-                    const double* foot_ref, const double* gamma, const double* mass, const double* k1,
-                    int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
-                    int32_t* status, int32_t* iters) {
+static int solve_host_impl(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
+                           const double* foot_ref, const double* gamma, const double* mass, const double* k1,
+                           int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
+                           int32_t* status, int32_t* iters, int32_t traj_batch, double* X, double* U, const char* who) {
   if (!h) return fail(-1, "cmpc_solve_host: null handle");
   if (batch < 1 || batch > h->cap) return fail(-1, "cmpc_solve_host: batch exceeds the handle's capacity");
   if (!x0 || !com_ref || !foot_ref || !gamma || !mass || !k1) return fail(-1, "cmpc_solve_host: null input pointer");
+  if (traj_batch < 0 || traj_batch > batch || (traj_batch > 0 && (!X || !U))) return fail(-1, "cmpc_solve_host_traj: bad trajectory arguments");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
+  if (traj_batch > 0) { if (int rc = ensure_traj(h)) return rc; }
   const int N = h->cfg.N; const size_t B = (size_t)batch;
   // pack inputs into one pinned buffer -> one H2D copy
   double* p = h->h_in;
   double* hx0 = p; p += B * NXP; double* hcom = p; p += B * 9 * N; double* hfoot = p; p += B * 8 * N;
   double* hgam = p; p += B * 2 * (N + 1); double* hm = p; p += B; double* hk = p; p += B;
+  if (int rc = order_after_last(h, h->stream)) return rc;
+  CK(cudaStreamSynchronize(h->stream), who);           // the pinned staging of a previous call must have been consumed
   memcpy(hx0, x0, B * NXP * sizeof(double)); memcpy(hcom, com_ref, B * 9 * N * sizeof(double));
   memcpy(hfoot, foot_ref, B * 8 * N * sizeof(double)); memcpy(hgam, gamma, B * 2 * (N + 1) * sizeof(double));
   memcpy(hm, mass, B * sizeof(double)); memcpy(hk, k1, B * sizeof(double));
@@ -355,7 +541,13 @@ int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const doubl
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->h_out, h->d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "D2H");
   CK(cudaMemcpyAsync(h->h_iout, h->d_iout, B * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream), "D2H");
-  CK(cudaStreamSynchronize(h->stream), "cmpc_solve_host: kernel execution");
+  const size_t TB = (size_t)traj_batch, nX = TB * (N + 1) * NXP, nU = TB * N * NU;
+  if (traj_batch > 0) {                                // the full primal trajectories ride on the same synchronisation
+    cmpc_export_traj<<<traj_batch, 128, 0, h->stream>>>(traj_batch, N, h->iter, h->istride, h->d_traj, h->d_traj + nX);
+    CK(cudaGetLastError(), "cmpc_export_traj launch");
+    CK(cudaMemcpyAsync(h->h_traj, h->d_traj, (nX + nU) * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "D2H");
+  }
+  CK(cudaStreamSynchronize(h->stream), who);
   const double* r = h->h_out;
   if (x1) memcpy(x1, r, B * NXP * sizeof(double)); r += B * NXP;
   if (u0) memcpy(u0, r, B * NU * sizeof(double)); r += B * NU;
@@ -364,53 +556,69 @@ int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const doubl
   if (viol) memcpy(viol, r, B * sizeof(double));
   if (status) memcpy(status, h->h_iout, B * sizeof(int32_t));
   if (iters) memcpy(iters, h->h_iout + B, B * sizeof(int32_t));
+  if (traj_batch > 0) { memcpy(X, h->h_traj, nX * sizeof(double)); memcpy(U, h->h_traj + nX, nU * sizeof(double)); }
   return 0;
+}
+
+int cmpc_solve_host(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
+                    const double* foot_ref, const double* gamma, const double* mass, const double* k1,
+                    int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
+                    int32_t* status, int32_t* iters) {
+  return solve_host_impl(h, batch, x0, com_ref, foot_ref, gamma, mass, k1, warm_mode, x1, u0, xN, cost, viol, status, iters, 0, nullptr, nullptr,
+                         "cmpc_solve_host: kernel execution");
+}
+
+int cmpc_solve_host_traj(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
+                         const double* foot_ref, const double* gamma, const double* mass, const double* k1,
+                         int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,
+                         int32_t* status, int32_t* iters, int32_t traj_batch, double* X, double* U) {
+  return solve_host_impl(h, batch, x0, com_ref, foot_ref, gamma, mass, k1, warm_mode, x1, u0, xN, cost, viol, status, iters, traj_batch, X, U,
+                         "cmpc_solve_host_traj: kernel execution");
 }
 
 int cmpc_get_trajectory(cmpc_handle* h, int32_t batch, double* X, double* U) {
   if (!h || !X || !U || batch < 1 || batch > h->cap) return fail(-1, "cmpc_get_trajectory: bad arguments");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
-  const int N = h->cfg.N; const size_t B = (size_t)batch;
-  double *dX, *dU;
-  CK(cudaMalloc(&dX, B * (N + 1) * NXP * sizeof(double)), "cudaMalloc");
-  CK(cudaMalloc(&dU, B * N * NU * sizeof(double)), "cudaMalloc");
-  cmpc_export_traj<<<batch, 128, 0, h->stream>>>(batch, N, h->work, h->wstride, dX, dU);
+  if (int rc = ensure_traj(h)) return rc;
+  if (int rc = order_after_last(h, h->stream)) return rc;
+  const int N = h->cfg.N; const size_t B = (size_t)batch, nX = B * (N + 1) * NXP, nU = B * N * NU;
+  cmpc_export_traj<<<batch, 128, 0, h->stream>>>(batch, N, h->iter, h->istride, h->d_traj, h->d_traj + nX);
   CK(cudaGetLastError(), "cmpc_export_traj launch");
-  CK(cudaMemcpyAsync(X, dX, B * (N + 1) * NXP * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "D2H");
-  CK(cudaMemcpyAsync(U, dU, B * N * NU * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "D2H");
+  CK(cudaMemcpyAsync(h->h_traj, h->d_traj, (nX + nU) * sizeof(double), cudaMemcpyDeviceToHost, h->stream), "D2H");
+  if (int rc = mark_done(h, h->stream)) return rc;
   CK(cudaStreamSynchronize(h->stream), "cmpc_get_trajectory");
-  cudaFree(dX); cudaFree(dU);
+  memcpy(X, h->h_traj, nX * sizeof(double)); memcpy(U, h->h_traj + nX, nU * sizeof(double));
   return 0;
 }
 
 int cmpc_set_warm(cmpc_handle* h, int32_t batch, const double* X, const double* U) {
   if (!h || !X || !U || batch < 1 || batch > h->cap) return fail(-1, "cmpc_set_warm: bad arguments");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
-  const int N = h->cfg.N; const size_t B = (size_t)batch;
-  double *dX, *dU;
-  CK(cudaMalloc(&dX, B * (N + 1) * NXP * sizeof(double)), "cudaMalloc");
-  CK(cudaMalloc(&dU, B * N * NU * sizeof(double)), "cudaMalloc");
-  CK(cudaMemcpyAsync(dX, X, B * (N + 1) * NXP * sizeof(double), cudaMemcpyHostToDevice, h->stream), "H2D");
-  CK(cudaMemcpyAsync(dU, U, B * N * NU * sizeof(double), cudaMemcpyHostToDevice, h->stream), "H2D");
-  cmpc_import_traj<<<batch, 128, 0, h->stream>>>(batch, N, h->work, h->wstride, dX, dU);
+  if (int rc = ensure_traj(h)) return rc;
+  if (int rc = order_after_last(h, h->stream)) return rc;
+  CK(cudaStreamSynchronize(h->stream), "cmpc_set_warm");          // pinned staging free
+  const int N = h->cfg.N; const size_t B = (size_t)batch, nX = B * (N + 1) * NXP, nU = B * N * NU;
+  memcpy(h->h_traj, X, nX * sizeof(double)); memcpy(h->h_traj + nX, U, nU * sizeof(double));
+  CK(cudaMemcpyAsync(h->d_traj, h->h_traj, (nX + nU) * sizeof(double), cudaMemcpyHostToDevice, h->stream), "H2D");
+  cmpc_import_traj<<<batch, 128, 0, h->stream>>>(batch, N, h->iter, h->istride, h->d_traj, h->d_traj + nX, h->d_valid);
   CK(cudaGetLastError(), "cmpc_import_traj launch");
+  if (int rc = mark_done(h, h->stream)) return rc;
   CK(cudaStreamSynchronize(h->stream), "cmpc_set_warm");
-  cudaFree(dX); cudaFree(dU);
-  h->warm_valid = batch;
   return 0;
 }
 
 int cmpc_warm_save(cmpc_handle* h, int32_t batch) {
   if (!h || batch < 1 || batch > h->cap) return fail(-1, "cmpc_warm_save: bad arguments");
-  if (h->warm_valid < batch) return fail(-1, "cmpc_warm_save: no warm-start state for that many instances");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
-  const int N = h->cfg.N;
-  h->iter_doubles = (size_t)(N + 1) * NX * 2 + (size_t)N * NU + (size_t)(N + 1) * NR * 2;   // X, U, Y, S, LAM
-  if (!h->snap) CK(cudaMalloc(&h->snap, (size_t)h->cap * h->iter_doubles * sizeof(double)), "cudaMalloc(snapshot)");
-  if (!h->snap_iters) CK(cudaMalloc(&h->snap_iters, (size_t)h->cap * sizeof(int32_t)), "cudaMalloc(snapshot iters)");
+  const size_t B = (size_t)h->cap;
+  if (!h->snap) CK(cudaMalloc(&h->snap, B * h->istride * sizeof(double)), "cudaMalloc(snapshot)");
+  if (!h->snap_iters) CK(cudaMalloc(&h->snap_iters, B * sizeof(int32_t)), "cudaMalloc(snapshot iters)");
+  if (!h->snap_valid) CK(cudaMalloc(&h->snap_valid, B * sizeof(int32_t)), "cudaMalloc(snapshot valid)");
+  if (int rc = order_after_last(h, h->stream)) return rc;
   CK(cudaMemcpyAsync(h->snap_iters, h->d_last_iters, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream), "snapshot iters");
-  CK(cudaMemcpy2DAsync(h->snap, h->iter_doubles * sizeof(double), h->work, h->wstride * sizeof(double),
-                       h->iter_doubles * sizeof(double), batch, cudaMemcpyDeviceToDevice, h->stream), "snapshot copy");
+  CK(cudaMemcpyAsync(h->snap_valid, h->d_valid, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream), "snapshot valid");
+  CK(cudaMemcpyAsync(h->snap, h->iter, (size_t)batch * h->istride * sizeof(double), cudaMemcpyDeviceToDevice, h->stream), "snapshot copy");
+  if (int rc = mark_done(h, h->stream)) return rc;
   CK(cudaStreamSynchronize(h->stream), "cmpc_warm_save");
   h->snap_batch = batch;
   return 0;
@@ -420,16 +628,24 @@ int cmpc_warm_restore(cmpc_handle* h, int32_t batch, void* stream) {
   if (!h || batch < 1 || batch > h->snap_batch) return fail(-1, "cmpc_warm_restore: no snapshot for that many instances");
   CK(cudaSetDevice(h->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
-  CK(cudaMemcpy2DAsync(h->work, h->wstride * sizeof(double), h->snap, h->iter_doubles * sizeof(double),
-                       h->iter_doubles * sizeof(double), batch, cudaMemcpyDeviceToDevice, s), "snapshot restore");
+  if (int rc = order_after_last(h, s)) return rc;
+  CK(cudaMemcpyAsync(h->iter, h->snap, (size_t)batch * h->istride * sizeof(double), cudaMemcpyDeviceToDevice, s), "snapshot restore");
   CK(cudaMemcpyAsync(h->d_last_iters, h->snap_iters, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, s), "snapshot restore iters");
-  h->warm_valid = batch;
-  return 0;
+  CK(cudaMemcpyAsync(h->d_valid, h->snap_valid, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, s), "snapshot restore valid");
+  return mark_done(h, s);
 }
 
-int cmpc_reset_warm(cmpc_handle* h) {
+int cmpc_reset_warm(cmpc_handle* h, const uint8_t* mask, int32_t n) {
   if (!h) return fail(-1, "cmpc_reset_warm: null handle");
-  h->warm_valid = 0;
+  if (mask && (n < 1 || n > h->cap)) return fail(-1, "cmpc_reset_warm: bad mask length");
+  CK(cudaSetDevice(h->device), "cudaSetDevice");
+  if (int rc = order_after_last(h, h->stream)) return rc;
+  const int cnt = mask ? n : h->cap;
+  if (mask) CK(cudaMemcpyAsync(h->d_mask, mask, (size_t)n, cudaMemcpyHostToDevice, h->stream), "H2D mask");
+  cmpc_clear_valid<<<(cnt + 255) / 256, 256, 0, h->stream>>>(cnt, mask ? h->d_mask : nullptr, h->d_valid);
+  CK(cudaGetLastError(), "cmpc_clear_valid launch");
+  if (int rc = mark_done(h, h->stream)) return rc;
+  CK(cudaStreamSynchronize(h->stream), "cmpc_reset_warm");         // (the caller's mask buffer may be pageable)
   return 0;
 }
 
@@ -459,10 +675,26 @@ int cmpc_phase_cycles(cmpc_handle* h, uint64_t* out11) {
   return 0;
 }
 
-int cmpc_footprint(const cmpc_handle* h, size_t* work_bytes_per_instance, size_t* smem_bytes_per_cta) {
+int cmpc_footprint(const cmpc_handle* h, size_t* iterate_bytes_per_instance, size_t* scratch_bytes_per_slot, int32_t* slots,
+                   size_t* smem_bytes_per_cta) {
   if (!h) return fail(-1, "cmpc_footprint: null handle");
-  if (work_bytes_per_instance) *work_bytes_per_instance = h->wstride * sizeof(double);
+  if (iterate_bytes_per_instance) *iterate_bytes_per_instance = h->istride * sizeof(double);
+  if (scratch_bytes_per_slot) *scratch_bytes_per_slot = h->sstride * sizeof(double);
+  if (slots) *slots = h->slots;
   if (smem_bytes_per_cta) *smem_bytes_per_cta = sizeof(Smem);
+  return 0;
+}
+
+int cmpc_assemble_device(const cmpc_walk_tables* tb, int32_t device, int32_t batch, const int32_t* tick, const double* com_pos,
+                         const double* com_vel, const double* hw, const double* theta, const double* yaw, const double* plan,
+                         double* x0, double* com_ref, double* foot_ref, double* gamma, int32_t* err, void* stream) {
+  if (!tb || batch < 1 || !tick || !com_pos || !com_vel || !hw || !theta || !yaw || !plan || !x0 || !com_ref || !foot_ref || !gamma)
+    return fail(-1, "cmpc_assemble_device: null argument");
+  if (tb->N < 1 || tb->N > NMAX || tb->rate < 1 || tb->n_steps < 1 || !tb->com_tab || !tb->foot_tab || !tb->gamma_tab || !tb->step_index)
+    return fail(-1, "cmpc_assemble_device: bad tables");
+  CK(cudaSetDevice(device), "cudaSetDevice");
+  cmpc_assemble_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(*tb, batch, tick, com_pos, com_vel, hw, theta, yaw, plan, x0, com_ref, foot_ref, gamma, err);
+  CK(cudaGetLastError(), "cmpc_assemble_kernel launch");
   return 0;
 }
 

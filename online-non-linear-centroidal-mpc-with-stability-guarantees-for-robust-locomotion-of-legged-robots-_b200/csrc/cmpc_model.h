@@ -28,10 +28,6 @@
 #define CMPC_HD inline
 #endif
 
-#ifndef CMPC_DEDUP_BOX
-#define CMPC_DEDUP_BOX 0
-#endif
-
 namespace cmpc {
 
 constexpr int NXP = 20;          // physical states (reference layout, MPC file :164-166)
@@ -59,9 +55,9 @@ struct Config {
   double mu_init, mu_final, tol, kappa_eps, kappa_mu, theta_mu, tau_min, bound_push;
   double mu_warm;                   // initial barrier for full warm starts
   double warm_push, warm_comp;      // full warm start: slack floor, and cap on s*lam/mu_warm (0 = none)
-  double warm_new_push;             // full warm start: slack floor of rows that were not active at this stage in the previous tick
   int max_iter, ls_max;
-  double xp[8];                     // experiment knobs (hostsim studies)
+  int stall_window;                 // iterations without halving the barrier-problem error before an attempt is abandoned (0 = off)
+  double xp[8];                     // experiment knobs (studies with the tests/hostsim build)
 };
 
 CMPC_HD Config default_config(int N) {
@@ -73,8 +69,9 @@ CMPC_HD Config default_config(int N) {
   c.pz_max = 0.76; c.box[0] = 0.01; c.box[1] = 0.005; c.box[2] = 0.00005;
   c.relax = 1e-8;
   c.mu_init = 0.1; c.mu_final = 1e-9; c.tol = 1e-8; c.kappa_eps = 10.0; c.kappa_mu = 0.2;
-  c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 1e-6; c.warm_comp = 0.0; c.warm_new_push = 1e-2;
+  c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 1e-6; c.warm_comp = 0.0;
   for (int j = 0; j < 8; ++j) c.xp[j] = 0.0;
+  c.stall_window = 60;
   c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
   return c;
 }
@@ -322,14 +319,8 @@ CMPC_HD void build_masks(const Config& c, const Instance& in, uint64_t* mask, do
     if (i >= 1) {
       for (int e = 0; e < 2; ++e) {
         if ((e ? gr : gl) < 0.5) continue;
-        if (moved[e]) {
-          // a foot that was already in stance at stage i-1 does not move into stage i ((1 - gamma) = 0 in :455-458): with
-          // an unchanged reference its box rows repeat those of stage i-1 exactly -- kept once, at the landing stage
-          const double* fr = in.foot_ref + 8 * (i - 1);
-          bool same = (i >= 2) && ((e ? in.gamma[2 * (i - 1) + 1] : in.gamma[2 * (i - 1)]) > 0.5) && ((mask[i - 1] >> (R_BOX + 6 * e)) & 1ull);
-          if (same) for (int j = 0; j < 3; ++j) same = same && (fr[3 * e + j] == fr[3 * e + j - 8]);
-          if (!same || !CMPC_DEDUP_BOX) mk |= 0x3Full << (R_BOX + 6 * e);
-        } else {
+        if (moved[e]) mk |= 0x3Full << (R_BOX + 6 * e);
+        else {
           const double* fr = in.foot_ref + 8 * (i - 1);
           for (int j = 0; j < 3; ++j) {
             const double err = fabs(in.x0[(e ? IPR : IPL) + j] - fr[3 * e + j]) - c.box[j];

@@ -9,13 +9,20 @@
 //                  32x32 input block, Schur complement = cost-to-go P_i; factors streamed to global
 //   forward pass   du_i = -L^-T (l_m + L_S' dx_i), dx_{i+1} = A dx_i + B du_i + d_i, costates
 //   line search    fraction-to-boundary + a short filter backtracking, evaluated thread-per-stage
-//   convergence    block-wide max/sum reductions (warp shuffles on the GPU)
+//   convergence    per-stage partial results reduced by warp 0 with shuffles (__shfl_xor_sync), NaN detection by a warp
+//                  vote, pivot tests by a barrier vote (__syncthreads_and)
 //
 // The code is written against an execution policy `Par` (tid, nt, sync, reductions) so the very same
 // source runs as one CTA per instance on sm_100a and as a single serial "thread" under g++ in
 // tests/hostsim (debug aid).  All arithmetic is FP64.
 #pragma once
 #include "cmpc_model.h"
+
+#if defined(__CUDACC__)
+#define CMPC_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CMPC_HD_NOINLINE
+#endif
 
 namespace cmpc {
 
@@ -110,27 +117,34 @@ CMPC_HD double cmpc_rsqrt(double x) {
 #endif
 }
 
-enum Status { ST_CONVERGED = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_INFEASIBLE_X0 = 4, ST_NAN = 5 };
+enum Status { ST_CONVERGED = 0, ST_MAXITER = 1, ST_LINESEARCH = 2, ST_REGULARIZATION = 3, ST_INFEASIBLE_X0 = 4, ST_NAN = 5, ST_STALL = 6 };
 
-// Global-memory workspace of one instance (device resident across ticks: warm starts).
+// Global memory of one solve.  The ITERATE (states, inputs, costates, slacks, multipliers) belongs to the instance and
+// stays device resident across ticks (warm starts); the Newton step, the per-stage derivative records and the stage
+// factors are SCRATCH of the resident CTA slot that happens to run the solve (0.4 MB at N = 20: with one scratch block per
+// slot instead of one per instance the working set of a launch is slots x 0.4 MB and mostly stays in L2).
 struct Work {
   double *X, *U, *Y, *S, *LAM;        // iterate: (N+1)*28, N*32, (N+1)*28, (N+1)*56, (N+1)*56
   double *DX, *DU, *DS, *YN, *DW;     // Newton step (YN = full-step costates, DW = new multipliers of explicit rows)
   double *REC, *FAC;                  // (N+1)*RECSZ, N*FACSZ
 };
 
-CMPC_HD size_t work_doubles(int N) {
-  return (size_t)(N + 1) * NX * 4 + (size_t)N * NU * 2 + (size_t)N * NW + (size_t)(N + 1) * NR * 3 + (size_t)(N + 1) * RECSZ + (size_t)N * FACSZ;
+CMPC_HD size_t iter_doubles(int N) { return (size_t)(N + 1) * NX * 2 + (size_t)N * NU + (size_t)(N + 1) * NR * 2; }
+CMPC_HD size_t scratch_doubles(int N) {
+  return (size_t)(N + 1) * NX * 2 + (size_t)N * NU + (size_t)N * NW + (size_t)(N + 1) * NR + (size_t)(N + 1) * RECSZ + (size_t)N * FACSZ;
 }
+CMPC_HD size_t work_doubles(int N) { return iter_doubles(N) + scratch_doubles(N); }
 
-CMPC_HD Work carve_work(double* base, int N) {
-  Work w; double* p = base;
+CMPC_HD Work carve_work(double* iter, double* scratch, int N) {
+  Work w; double* p = iter;
   w.X = p; p += (N + 1) * NX;  w.U = p; p += N * NU;  w.Y = p; p += (N + 1) * NX;
-  w.S = p; p += (N + 1) * NR;  w.LAM = p; p += (N + 1) * NR;
+  w.S = p; p += (N + 1) * NR;  w.LAM = p;
+  p = scratch;
   w.DX = p; p += (N + 1) * NX; w.DU = p; p += N * NU; w.DS = p; p += (N + 1) * NR; w.YN = p; p += (N + 1) * NX; w.DW = p; p += N * NW;
   w.REC = p; p += (size_t)(N + 1) * RECSZ; w.FAC = p;
   return w;
 }
+CMPC_HD Work carve_work(double* base, int N) { return carve_work(base, base + iter_doubles(N), N); }   // one contiguous block (tests/hostsim)
 
 // Shared-memory block of one instance.
 struct alignas(16) Smem {
@@ -145,6 +159,7 @@ struct alignas(16) Smem {
   double rdiag[NA];          // reciprocal of the stored diagonal of L
   double lyapC[16];          // curvature of the Lyapunov row in (p, v, theta, F) space (per instance)
   double red[2];
+  double red5[5];            // block-wide reduction results (written by lane 0 of warp 0)
   uint64_t mask[NMAX + 1];
   double acc[NMAX + 1][5];   // per-stage partial results of the eval / slack-step / trial passes
   int flag;
@@ -536,24 +551,6 @@ struct Solver {
         const int i = t / NR, r = t % NR;
         if (!(sm.mask[i] & (1ull << r))) { gS()[t] = 1.0; gLAM()[t] = 0.0; continue; }
         double sv = gS()[t], lv = gLAM()[t];
-        if (c.warm_new_push > 0.0 && sv == 1.0 && lv == 0.0) {
-          // the row was not part of the previous tick's problem at this stage (the contact schedule moved on): start its
-          // slack from the row's value at the warm point, like a cold start does, with the multiplier on the central path
-          double gv = 0.0;
-          if (r >= R_FRIC && r < R_UNI) {
-            const int v = (r - R_FRIC) >> 2, q = (r - R_FRIC) & 3;
-            const double* f = gU() + i * NU + 3 * v;
-            gv = ((q & 1) ? -1.0 : 1.0) * f[q >> 1] - c.mu_fric * f[2];
-          } else if (r >= R_UNI && r < R_BOX) {
-            gv = -gU()[i * NU + 3 * (r - R_UNI) + 2];
-          } else if (r >= R_BOX) {
-            const int e = (r - R_BOX) / 6, q = (r - R_BOX) % 6, j = q >> 1;
-            const double err = gX()[i * NX + (e ? IPR : IPL) + j] - i_foot_ref()[8 * (i - 1) + 3 * e + j];
-            gv = ((q & 1) ? -err : err) - c.box[j];
-          }
-          sv = c.relax - gv; sv = sv > c.warm_new_push ? sv : c.warm_new_push;
-          lv = mu / sv;
-        }
         if (!(sv > c.warm_push)) sv = c.warm_push;
         if (!(lv > mu / sv * 1e-3)) lv = mu / sv * 1e-3;
         if (c.warm_comp > 0.0 && lv > mu / sv * c.warm_comp) lv = mu / sv * c.warm_comp;
@@ -898,19 +895,28 @@ struct Solver {
     reduce_acc(out);
   }
 
-  // tiny reduction over <= 65 stages done redundantly by every thread (broadcast reads)
+  // reduction over the <= 65 stages by warp 0: lanes stride the stages, shuffle tree across the lanes, a warp vote carries
+  // NaNs (a NaN never wins a comparison), lane 0 publishes
   CMPC_HD void reduce_acc(double* out) {
     Smem& sm = par.template smem<Smem>();
     const int N = c.N;
-    double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0;
-    for (int i = 0; i <= N; ++i) {
-      const double* a = sm.acc[i];
-      prim = a[0] > prim ? a[0] : prim; dual = a[1] > dual ? a[1] : dual;
-      smax = a[2] > smax ? a[2] : smax; smin = a[3] < smin ? a[3] : smin;
-      ssum += a[4];
+    if (par.warp() == 0) {
+      double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0;
+      bool bad = false;
+      for (int i = par.lane(); i <= N; i += par.lanes()) {
+        const double* a = sm.acc[i];
+        bad = bad || !(a[0] == a[0]) || !(a[1] == a[1]);
+        prim = a[0] > prim ? a[0] : prim; dual = a[1] > dual ? a[1] : dual;
+        smax = a[2] > smax ? a[2] : smax; smin = a[3] < smin ? a[3] : smin;
+        ssum += a[4];
+      }
+      prim = par.wmax(prim); dual = par.wmax(dual); smax = par.wmax(smax); smin = par.wmin(smin); ssum = par.wsum(ssum);
+      if (par.any(bad)) prim = nan("");
+      if (par.lane() == 0) { sm.red5[0] = prim; sm.red5[1] = dual; sm.red5[2] = smax; sm.red5[3] = smin; sm.red5[4] = ssum; }
     }
-    out[0] = prim; out[1] = dual; out[2] = smax; out[3] = smin; out[4] = ssum; out[5] = 0.0; out[6] = 0.0; out[7] = 0.0;
     par.sync();
+    out[0] = sm.red5[0]; out[1] = sm.red5[1]; out[2] = sm.red5[2]; out[3] = sm.red5[3]; out[4] = sm.red5[4]; out[5] = 0.0; out[6] = 0.0; out[7] = 0.0;
+    // (no barrier here: red5 / acc are next written behind at least one barrier of the following pass)
   }
 
   CMPC_HD int n_rows_total() const {
@@ -1147,7 +1153,7 @@ struct Solver {
         }
         bool okp = true;
         // factor a diagonal tile held in registers; publish {1/d0..1/d3, l10, l20, l21, l30, l31, l32} and the pivot test
-        auto diag_tile = [&](double (&t)[16], int tk) {
+        auto diag_tile = [&](double (&t)[16], int tk) -> bool {
           // two 2 x 2 steps: in each, rsqrt(a) and rsqrt(a c - b^2) are independent and branch-free, so they interleave and
           // the dependent chain holds two rsqrt latencies instead of four (second pivot of a step = (a c - b^2) / a, its
           // reciprocal root = a rsqrt(a) rsqrt(a c - b^2))
@@ -1164,16 +1170,17 @@ struct Solver {
           const double i2 = cmpc_rsqrt_nb(p2), r3 = cmpc_rsqrt_nb(det2);
           const double p3 = det2 * (i2 * i2), i3 = r3 * (p2 * i2);
           const double l32 = b2 * i2;
-          const bool good = p0 > 1e-14 && p1 > 1e-14 && p2 > 1e-14 && p3 > 1e-14;
+          // (upper bounds: the single-precision seed of cmpc_rsqrt_nb overflows beyond ~1e38 and would return 0 silently)
+          const bool good = p0 > 1e-14 && p1 > 1e-14 && p2 > 1e-14 && p3 > 1e-14 && p0 < 1e30 && p2 < 1e30 && det1 < 1e36 && det2 < 1e36;
 #ifdef CMPC_TRACE
           if (cmpc_trace_on && !good) printf("   pivot fail stage %d block %d piv %.3e %.3e %.3e %.3e reg %.1e\n", i, tk, p0, p1, p2, p3, reg);
 #endif
-          sm.flag = good ? 1 : 0;
           double* d = sm.dpub;
           d[0] = i0; d[1] = i1; d[2] = i2; d[3] = i3; d[4] = l10; d[5] = l20; d[6] = l21; d[7] = l30; d[8] = l31; d[9] = l32;
           sm.rdiag[4 * tk] = i0; sm.rdiag[4 * tk + 1] = i1; sm.rdiag[4 * tk + 2] = i2; sm.rdiag[4 * tk + 3] = i3;
           t[0] = p0 * i0; t[4] = l10; t[5] = p1 * i1; t[8] = l20; t[9] = l21; t[10] = p2 * i2;
           t[12] = l30; t[13] = l31; t[14] = l32; t[15] = p3 * i3;
+          return good;
         };
         // rows of L of a tile below the diagonal tile (in place), published as tile row `ti` of the panel
         auto panel_tile = [&](double (&t)[16], int ti) {
@@ -1198,6 +1205,7 @@ struct Solver {
         {   // ---- block 0: tile column 0 (transient tiles)
           double C[Par::CPT][16];
           int ci_[Par::CPT];
+          bool mygood = true;
           const int cbase = nt >= 16 ? nt - 16 : 0;
 #pragma unroll
           for (int sl = 0; sl < Par::CPT; ++sl) {
@@ -1211,11 +1219,10 @@ struct Solver {
                   const int r = 4 * ci_[sl] + a_;
                   C[sl][4 * a_ + b_] = (r < MROWS && b_ <= r) ? sm.M[mi(r, b_)] : 0.0;
                 }
-              if (ci_[sl] == 0) diag_tile(C[sl], 0);
+              if (ci_[sl] == 0) mygood = diag_tile(C[sl], 0);
             }
           }
-          par.sync();                                               // A
-          if (!sm.flag) okp = false;
+          if (!par.sync_and(mygood)) okp = false;                   // A: barrier + vote on the pivot test
           if (okp) {
 #pragma unroll
             for (int sl = 0; sl < Par::CPT; ++sl) {
@@ -1233,11 +1240,11 @@ struct Solver {
         }
         for (int tk = 0; tk < NU / 4 && okp; ++tk) {
           if (tk > 0) {
+            bool mygood = true;
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl)
-              if (ti_[sl] == tk && tj_[sl] == tk) diag_tile(T[sl], tk);
-            par.sync();                                             // A
-            if (!sm.flag) { okp = false; break; }                   // uniform
+              if (ti_[sl] == tk && tj_[sl] == tk) mygood = diag_tile(T[sl], tk);
+            if (!par.sync_and(mygood)) { okp = false; break; }      // A: barrier + vote (uniform result)
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl)
               if (tj_[sl] == tk && ti_[sl] > tk) panel_tile(T[sl], ti_[sl]);
@@ -1533,13 +1540,17 @@ struct Solver {
       sm.acc[i][0] = ap; sm.acc[i][1] = ad; sm.acc[i][2] = gd; sm.acc[i][3] = dsos;
     }
     par.sync();
-    double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
-    for (int i = 0; i <= N; ++i) {
-      ap = sm.acc[i][0] < ap ? sm.acc[i][0] : ap; ad = sm.acc[i][1] < ad ? sm.acc[i][1] : ad;
-      gd += sm.acc[i][2]; dsos += sm.acc[i][3];
+    if (par.warp() == 0) {
+      double ap = 1.0, ad = 1.0, gd = 0.0, dsos = 0.0;
+      for (int i = par.lane(); i <= N; i += par.lanes()) {
+        ap = sm.acc[i][0] < ap ? sm.acc[i][0] : ap; ad = sm.acc[i][1] < ad ? sm.acc[i][1] : ad;
+        gd += sm.acc[i][2]; dsos += sm.acc[i][3];
+      }
+      ap = par.wmin(ap); ad = par.wmin(ad); gd = par.wsum(gd); dsos = par.wsum(dsos);
+      if (par.lane() == 0) { sm.red5[0] = ap; sm.red5[1] = ad; sm.red5[2] = gd; sm.red5[3] = dsos; }
     }
-    *a_p = ap; *a_d = ad; *dphi = gd - mu * dsos;
     par.sync();
+    *a_p = sm.red5[0]; *a_d = sm.red5[1]; *dphi = sm.red5[2] - mu * sm.red5[3];
   }
 
   // ---- trial point (x + a dx, u + a du, s + a ds) for the line search: constraint violation theta, cost (with and
@@ -1714,13 +1725,17 @@ struct Solver {
   CMPC_HD void reduce_trial(double* out) {
     Smem& sm = par.template smem<Smem>();
     const int N = c.N;
-    double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
-    for (int i = 0; i <= N; ++i) {
-      theta += sm.acc[i][0]; cost += sm.acc[i][1]; lns += sm.acc[i][2];
-      viol = sm.acc[i][3] > viol ? sm.acc[i][3] : viol; cref += sm.acc[i][4];
+    if (par.warp() == 0) {
+      double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
+      for (int i = par.lane(); i <= N; i += par.lanes()) {
+        theta += sm.acc[i][0]; cost += sm.acc[i][1]; lns += sm.acc[i][2];
+        viol = sm.acc[i][3] > viol ? sm.acc[i][3] : viol; cref += sm.acc[i][4];
+      }
+      theta = par.wsum(theta); cost = par.wsum(cost); lns = par.wsum(lns); viol = par.wmax(viol); cref = par.wsum(cref);
+      if (par.lane() == 0) { sm.red5[0] = theta; sm.red5[1] = cost; sm.red5[2] = lns; sm.red5[3] = viol; sm.red5[4] = cref; }
     }
-    out[0] = theta; out[1] = cost; out[2] = lns; out[3] = viol; out[4] = cref;
     par.sync();
+    out[0] = sm.red5[0]; out[1] = sm.red5[1]; out[2] = sm.red5[2]; out[3] = sm.red5[3]; out[4] = sm.red5[4];
   }
 
   CMPC_HD void apply_step(double alpha, double a_d) {
@@ -1801,6 +1816,14 @@ struct Solver {
     par.sync();
   }
 
+  // one attempt (a launch pass of the CUDA path: the retries of failed instances are separate, compact launches there)
+  CMPC_HD void run_pass(int warm, double scale, Stats* st) {
+    setup();
+    mu_scale = scale; mu = 0; reg_last = 0;
+    run_once(warm, st);
+  }
+
+  // all attempts in sequence (host build of the core, tests/hostsim)
   CMPC_HD void run(int warm, Stats* st) {
     setup();
     // attempts: as asked (warm or cold, mu_init) -> cold, mu_init -> cold, 10 mu_init -> cold, mu_init / 10
@@ -1817,8 +1840,8 @@ struct Solver {
     }
   }
 
-  // ---- the interior-point loop
-  CMPC_HD void run_once(int warm, Stats* st) {
+  // ---- the interior-point loop (kept a function of its own on the device: inlined into the kernel it costs kilobytes of spills)
+  CMPC_HD_NOINLINE void run_once(int warm, Stats* st) {
     Smem& sm = par.template smem<Smem>();
     const int N = c.N;
     double pviol;
@@ -1831,7 +1854,8 @@ struct Solver {
     double ev[8], parts[3];
     double filt[16][2]; int nfilt = 0;
     double theta_max = 0, theta_min = 0; bool have_theta0 = false;
-    int status = ST_MAXITER, it = 0, ls_fail = 0;
+    int status = ST_MAXITER, it = 0, ls_fail = 0, stall_it = 0;
+    double stall_ref = -1.0;
     double kkt = 0.0;
     // merit quantities of the current point (constraint violation theta, cost, sum ln s): evaluated once here, afterwards
     // they are the values of the accepted trial point -- the eval pass needs no logarithms
@@ -1855,6 +1879,19 @@ struct Solver {
         double m1 = c.kappa_mu * mu, m2 = pow(mu, c.theta_mu);
         mu = m1 < m2 ? m1 : m2; if (mu < c.mu_final) mu = c.mu_final;
         nfilt = 0;
+        stall_it = it; stall_ref = -1.0;
+      }
+      // stall test: an attempt whose barrier-problem error has not halved within `stall_window` iterations at one barrier
+      // value is abandoned (it would run to max_iter: jammed at a saddle of the non-convex NLP, or diverging); the caller
+      // retries from another start
+      if (c.stall_window > 0) {
+        double p2[3];
+        const double emu = kkt_error(ev, mu, nrows, p2);
+        if (stall_ref < 0.0) { stall_ref = emu; stall_it = it; }
+        else if (it - stall_it >= c.stall_window) {
+          if (emu > 0.5 * stall_ref) { status = ST_STALL; break; }
+          stall_ref = emu; stall_it = it;
+        }
       }
       const double tau = (1.0 - mu) > c.tau_min ? (1.0 - mu) : c.tau_min;
       // factorise, regularising as IPOPT does when the input block is not positive definite

@@ -21,7 +21,7 @@ def build(force: bool = False) -> str:
         raise ImportError("oracle/_gen/stage_gen.c is missing (python -m oracle.gen_c)")
     if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-march=native", "-shared", "-fPIC", "-o", SO, srcs[0], "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-shared", "-fPIC", "-o", SO, srcs[0], "-lm"])
     return SO
 
 
@@ -33,10 +33,13 @@ def lib():
     return _lib
 
 
+ORACLE_R = dict(tol=1e-3, mu_final=1e-4, ipopt_termination=1, max_iter=1000)     # the reference's IPOPT options (MPC file :128), defaults otherwise
+
+
 def solve_packed(N, x0, com_ref, foot_ref, gamma, mass, k1, warm=None, **opts):
     """Instance-major arrays of the C ABI -> dict(status, iters, cost, viol, x1, u0, X, U).  `warm` = (X, U) primal warm start."""
     L = lib()
-    keys = ["tol", "mu_init", "mu_final", "relax", "max_iter", "ls_max", "eps_reg", "w_rate"]
+    keys = ["tol", "mu_init", "mu_final", "relax", "max_iter", "ls_max", "eps_reg", "w_rate", "ipopt_termination"]
     o = np.full(len(keys), np.nan)
     for k, v in opts.items():
         o[keys.index(k)] = v

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.." || exit 1
 P=online-non-linear-centroidal-mpc-with-stability-guarantees-for-robust-locomotion-of-legged-robots-_b200
 name=$1; shift
-mkdir -p scratch_libs
+mkdir -p lib/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -diag-suppress 170 -Xptxas -v \
-  -shared -Xcompiler -fPIC "$@" -o scratch_libs/lib_$name.so $P/csrc/cmpc_kernels.cu 2>&1 | grep -A3 "Compiling entry function.*cmpc_solve_kernel" | grep -E "stack|Used" | tr '\n' ' ' | sed "s/^/$name: /"
+  -shared -Xcompiler -fPIC "$@" -o lib/variants/lib_$name.so $P/csrc/cmpc_kernels.cu 2>&1 | grep -A3 "Compiling entry function.*cmpc_solve_kernel" | grep -E "stack|Used" | tr '\n' ' ' | sed "s/^/$name: /"
 echo

@@ -23,6 +23,11 @@ struct ParSerial {
   int nwarps() const { return 1; }
   int lanes() const { return 1; }
   void sync_warp() const {}
+  bool sync_and(bool p) const { return p; }
+  bool any(bool p) const { return p; }
+  double wmax(double v) const { return v; }
+  double wmin(double v) const { return v; }
+  double wsum(double v) const { return v; }
   void copy_async(double* dst, const double* src, int n) const { for (int t = 0; t < n; ++t) dst[t] = src[t]; }
   void commit_async() const {}
   void wait_async() const {}
@@ -35,7 +40,7 @@ void hostsim_trace(int on) { cmpc::cmpc_trace_on = on; }
 
 int hostsim_work_doubles(int N) { return (int)work_doubles(N); }
 
-// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min, warm_push, warm_comp, warm_new_push} (NaN = keep default)
+// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min, warm_push, warm_comp, xp0..xp7} (NaN = keep default)
 // Debug: stage-i Lagrangian gradient (60) and assembled stage block M (60x60, lower) at the iterate stored in
 // `work` (X, U, Y, S, LAM as laid out by carve_work).  Used by tests to check the analytic Hessian by finite
 // differences of the analytic gradient.
@@ -143,8 +148,8 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[12] == cfg_over[12]) c.tau_min = cfg_over[12];
     if (cfg_over[13] == cfg_over[13]) c.warm_push = cfg_over[13];
     if (cfg_over[14] == cfg_over[14]) c.warm_comp = cfg_over[14];
-    if (cfg_over[15] == cfg_over[15]) c.warm_new_push = cfg_over[15];
-    for (int j = 0; j < 8; ++j) if (cfg_over[16 + j] == cfg_over[16 + j]) c.xp[j] = cfg_over[16 + j];
+    if (cfg_over[23] == cfg_over[23]) c.stall_window = (int)cfg_over[23];
+    for (int j = 0; j < 8; ++j) if (cfg_over[15 + j] == cfg_over[15 + j]) c.xp[j] = cfg_over[15 + j];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);

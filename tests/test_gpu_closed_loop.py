@@ -43,7 +43,8 @@ def _oracle_mpc(initial, planner, params, com_ref, k1=None):
     return RefMPC(initial, planner, params, com_ref, solver=solver, k1=k1, k2=0.1)
 
 
-@pytest.mark.parametrize("N,t0,t1", [(10, 0, 60), (10, 180, 330)])
+# (20, 0, 1100): 1100 ticks at the benchmark horizon from the standing start through nine steps and the whole push window 800 < t < 900
+@pytest.mark.parametrize("N,t0,t1", [(10, 0, 60), (10, 180, 330), (20, 0, 1100)])
 def test_closed_loop_com_within_1mm(pkg, N, t0, t1):
     from oracle.mpc_ref import surrogate_walk
     from oracle.walk import load_walk

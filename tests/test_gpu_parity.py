@@ -63,6 +63,76 @@ def test_warm_start_modes_agree(pkg, golden):
     assert full["iters"][ok].mean() < 0.5 * cold["iters"][ok].mean()
 
 
+def test_shifted_and_automatic_warm_start_on_consecutive_ticks(pkg, walk_ticks):
+    """WARM_SHIFTED (3) and WARM_AUTO (4) on consecutive ticks of the recorded walk: same KKT points as a cold solve of
+    the same tick (cost 1e-6) for every tick that converges both ways, and cheaper than cold on average."""
+    N = 20
+    w = walk_ticks[N]
+    ticks = np.array([150, 199, 230, 255, 262, 268, 271, 300, 640, 805, 1455, 1700])
+    B = len(ticks)
+    args = lambda tt: (w["x0"][tt], w["com_ref"][tt], w["foot_ref"][tt], w["gamma"][tt], float(w["mass"]), float(w["k1"]))
+    cold = pkg.BatchSolver(N, B, device=0).solve_host(*args(ticks), 0)
+    assert (cold["status"] == 0).all()
+    for mode in (3, 4):
+        s = pkg.BatchSolver(N, B, device=0)
+        s.solve_host(*args(ticks - 1), 0)
+        o = s.solve_host(*args(ticks), mode)
+        assert (o["status"] == 0).all(), (mode, o["status"])
+        assert o["viol"].max() <= VIOL_TOL
+        same = cost_err(o["cost"], cold["cost"]) <= COST_TOL
+        assert same.sum() >= B - 2, (mode, cost_err(o["cost"], cold["cost"]))          # (a non-convex NLP: a tick may have a second KKT point)
+        assert cost_err(o["cost"], cold["cost"]).max() <= 1e-4
+        assert o["iters"].mean() < cold["iters"].mean()
+
+
+def test_reset_warm_mask_and_retry_accounting(pkg, golden):
+    """cmpc_reset_warm with a per-instance mask: flagged instances start cold on the next warm solve (same iteration
+    count as a cold solve), the others keep their warm start."""
+    g = golden[10]
+    B = len(g["ticks"])
+    args = (g["x0"], g["com_ref"], g["foot_ref"], g["gamma"], float(g["mass"]), float(g["k1"]))
+    s = pkg.BatchSolver(10, B, device=0)
+    cold = s.solve_host(*args, 0)
+    warm = s.solve_host(*args, 2)
+    mask = np.zeros(B, bool); mask[::2] = True
+    s.reset_warm(mask)
+    mixed = s.solve_host(*args, 2)
+    ok = cold["status"] == 0
+    assert np.array_equal(mixed["iters"][mask & ok], cold["iters"][mask & ok])          # cold again, bit for bit the same solve
+    assert np.array_equal(mixed["cost"][mask & ok], cold["cost"][mask & ok])
+    assert (mixed["iters"][~mask & ok] <= warm["iters"][~mask & ok] + 2).all()
+    s.reset_warm()
+    again = s.solve_host(*args, 2)
+    assert np.array_equal(again["iters"][ok], cold["iters"][ok])
+
+
+def test_operations_on_different_streams_are_ordered(pkg, golden):
+    """A solve on a user stream followed by handle-stream operations (trajectory export, snapshot) and back: the handle
+    orders them (no explicit synchronisation by the caller)."""
+    import torch
+    g = golden[10]
+    B = len(g["ticks"])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float64), device=dev)
+    s = pkg.BatchSolver(10, B, device=0)
+    ins = (t(g["x0"]), t(g["com_ref"]), t(g["foot_ref"]), t(g["gamma"]), t(np.full(B, float(g["mass"]))), t(np.full(B, float(g["k1"]))))
+    user = torch.cuda.Stream(dev)
+    with torch.cuda.stream(user):
+        out = s.solve_device(*ins, 0, stream=user.cuda_stream)
+    X, U = s.trajectory(B)                                   # handle's own stream: must see the finished solve
+    torch.cuda.synchronize()
+    assert np.abs(X[:, 1] - out["x1"].cpu().numpy()).max() == 0.0 and np.abs(U[:, 0] - out["u0"].cpu().numpy()).max() == 0.0
+    s.warm_save(B)
+    with torch.cuda.stream(user):
+        out2 = s.solve_device(*ins, 2, stream=user.cuda_stream)
+    s.warm_restore(B)                                        # handle's stream, ordered after the solve on `user`
+    with torch.cuda.stream(user):
+        out3 = s.solve_device(*ins, 2, stream=user.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out2["iters"].cpu().numpy(), out3["iters"].cpu().numpy())     # same snapshot, same warm solve
+    assert np.abs(out2["cost"].cpu().numpy() - out3["cost"].cpu().numpy()).max() == 0.0
+
+
 def test_device_entry_point_matches_host_entry_point(pkg, golden):
     import torch
     g = golden[10]
