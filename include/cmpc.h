@@ -97,7 +97,8 @@ const char* cmpc_version(void);
  * default stream.  Every operation on a handle is ordered after the previous operation on that handle, whatever streams
  * the two were issued on (the handle records an event behind each operation and later operations wait for it).
  * The warm-start state lives in the handle.  Instances that do not converge are solved again by up to three compact
- * follow-up launches (cold start, other initial barrier values); `iters` accumulates over the attempts. */
+ * follow-up launches (cold start; then a ten times larger initial barrier value; then another starting point, CoM states blended
+ * towards the reference along the horizon); `iters` accumulates over the attempts. */
 int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
                       const double* foot_ref, const double* gamma, const double* mass, const double* k1,
                       int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,

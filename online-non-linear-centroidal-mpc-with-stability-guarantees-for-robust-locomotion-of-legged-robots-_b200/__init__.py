@@ -17,8 +17,8 @@ from ._lib import BatchSolver, CmpcError, WalkTables, build_library, library_pat
 from .assembly import PlanTables, assemble_tick, pack_instances  # noqa: F401
 from .parallel import gather_stats, shard_arrays, shard_range  # noqa: F401
 from .fleet import Fleet  # noqa: F401
-from .com_reference import quintic_coefficients, references_from_knots, sample_tables  # noqa: F401
+from .com_reference import compute_knot, quintic_coefficients, references, references_from_knots, sample_tables  # noqa: F401
 
 __all__ = ["BatchSolver", "CmpcError", "WalkTables", "build_library", "library_path", "measure_fp64_peak",
            "PlanTables", "assemble_tick", "pack_instances", "gather_stats", "shard_arrays", "shard_range", "Fleet",
-           "quintic_coefficients", "references_from_knots", "sample_tables"]
+           "quintic_coefficients", "references_from_knots", "sample_tables", "compute_knot", "references"]

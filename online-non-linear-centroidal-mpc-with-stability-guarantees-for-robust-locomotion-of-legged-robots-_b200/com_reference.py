@@ -15,14 +15,74 @@ Restated behaviour (file:line of the reference):
     the derivative with respect to tau, NOT divided by the segment length (:222); the acceleration IS divided by the
     segment length squared (:243); the tables stop at sequence[-1], so x/z and y have different lengths.
   * z reference: constant 0.72 with zero velocity / acceleration, as long as the x table (:97-99).
-The knots and tick sequences themselves come from the reference's `compute_knot` (it queries the foot trajectory
-generator, which the drop-in leaves untouched).
+  * `compute_knot` (`functions.py:11-56`): the knots are mid-points of the two feet (x) and 0.6 x the lateral position
+    of the NEXT support foot (y), sampled one tick after every landing (ticks first_time_knot + ss + 1 + k (ss + ds)), with
+    two leading knots from the initial stance; the segment end ticks are those ticks for x and ds - 1 ticks later for y.
+    The foot positions it reads come from `FootTrajectoryGenerator.generate_feet_trajectories_at_time`
+    (`foot_trajectory_generator.py:12-116`); the x / y components of that function are restated in `feet_xy_at` (initial
+    pose during step 0, planned poses in double support, the cubic swing profile in single support), so the generator is
+    not needed to make references for another walk.
 """
 from __future__ import annotations
 
 import numpy as np
 
 COM_HEIGHT_REF = 0.72        # functions.py:97
+
+
+def _step_index_at(plan, time):
+    """`FootstepPlanner.get_step_index_at_time` (footstep_planner_vertices.py:82-88)."""
+    t = 0
+    for i, step in enumerate(plan):
+        t += step["ss_duration"] + step["ds_duration"]
+        if t > time:
+            return i
+    return None
+
+
+def feet_xy_at(plan, initial, time):
+    """x, y of both feet at tick `time`: {'lfoot': (x, y), 'rfoot': (x, y)} -- the `['pos'][3:5]` entries of
+    `generate_feet_trajectories_at_time` (foot_trajectory_generator.py:12-116)."""
+    idx = _step_index_at(plan, time)
+    if idx == 0:                                                     # :21-35 initial poses during the first step
+        return {"lfoot": tuple(np.asarray(initial["lfoot"]["pos"], float)[3:5]), "rfoot": tuple(np.asarray(initial["rfoot"]["pos"], float)[3:5])}
+    start = sum(s["ss_duration"] + s["ds_duration"] for s in plan[:idx])
+    tin = time - start
+    support = plan[idx]["foot_id"]
+    swing = "lfoot" if support == "rfoot" else "rfoot"
+    T = plan[idx]["ss_duration"]
+    if tin >= T:                                                     # :38-59 double support: planned poses
+        return {support: tuple(np.asarray(plan[idx]["pos"], float)[0:2]), swing: tuple(np.asarray(plan[idx + 1]["pos"], float)[0:2])}
+    a, b = np.asarray(plan[idx - 1]["pos"], float), np.asarray(plan[idx + 1]["pos"], float)      # :62-76 cubic swing profile
+    sft = -2.0 / T ** 3 * tin ** 3 + 3.0 / T ** 2 * tin ** 2
+    sw = a + (b - a) * sft
+    return {support: tuple(np.asarray(plan[idx]["pos"], float)[0:2]), swing: (sw[0], sw[1])}
+
+
+def compute_knot(plan, initial):
+    """knot_x, knot_y, sequence_x, sequence_y of `functions.compute_knot` (functions.py:11-56), from the plan alone."""
+    ss, ds = plan[2]["ss_duration"], plan[2]["ds_duration"]          # :17-18
+    f0 = feet_xy_at(plan, initial, 0)
+    knot_x = [(f0["lfoot"][0] + f0["rfoot"][0]) / 2, (f0["lfoot"][0] + f0["rfoot"][0]) / 2]      # :20, :23
+    knot_y = [(f0["lfoot"][1] + f0["rfoot"][1]) / 2, f0[plan[1]["foot_id"]][1] * 0.6]            # :21, :24-25
+    scale = ss + ds
+    first = int(2 * scale)                                           # :28-29
+    seq_x, seq_y = [first], [first]
+    first_contact = first + ss + 1                                   # :33
+    for i in range(first, len(plan) * scale - 1):                    # :35
+        if (i - first_contact) % scale == 0:
+            f = feet_xy_at(plan, initial, i)
+            knot_x.append((f["lfoot"][0] + f["rfoot"][0]) / 2)
+            seq_x.append(i)
+            contact = plan[_step_index_at(plan, i) + 1]["foot_id"]   # :41-45
+            knot_y.append(f[contact][1] * 0.6)
+            seq_y.append(i + ds - 1)                                 # :49
+    return knot_x, knot_y, seq_x, seq_y
+
+
+def references(plan, initial):
+    """`functions.references` (functions.py:58-124) end to end: knots from the plan, minimum-norm quintic splines, tables."""
+    return references_from_knots(*compute_knot(plan, initial))
 
 
 def spline_system(knots):

@@ -88,13 +88,13 @@ struct Outputs {
 // instances from an atomic work counter in list order; the scratch (Newton step, derivative records, stage factors)
 // belongs to the CTA slot, only the iterate belongs to the instance.  Pass 0 solves every instance as asked (warm or
 // cold); an instance that does not converge is appended to `list_out` and solved again by the next pass from the
-// solver's own cold start with another initial barrier value (mu_scale) -- a second, compact launch over the failed
+// solver's own cold start with another initial barrier value (mu_scale) or starting point (blend) -- a second, compact launch over the failed
 // subset instead of a retry loop inside the CTA, which left every other slot waiting for the few long ones.
 __global__ void __launch_bounds__(CMPC_THREADS, CMPC_MIN_CTAS)
 cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const double* __restrict__ com_ref,
                   const double* __restrict__ foot_ref, const double* __restrict__ gamma,
                   const double* __restrict__ mass, const double* __restrict__ k1, double* iter, size_t istride,
-                  double* scratch, size_t sstride, int warm, double mu_scale, int accumulate, Outputs out,
+                  double* scratch, size_t sstride, int warm, double mu_scale, int blend, int accumulate, Outputs out,
                   const int32_t* __restrict__ list_in, const int32_t* __restrict__ count_in, int32_t* __restrict__ list_out,
                   int32_t* count_out, int32_t* next, int32_t* __restrict__ last_iters, int32_t* __restrict__ valid) {
   Smem& sm = *reinterpret_cast<Smem*>(cmpc_smem_raw);
@@ -127,7 +127,7 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
 #ifdef CMPC_PROFILE
     const long long solve_t0 = clock64();
 #endif
-    sol.run_pass(wm, mu_scale, &st);
+    sol.run_pass(wm, mu_scale, &st, blend != 0);
     __syncthreads();
 #ifdef CMPC_PROFILE
     if (threadIdx.x == 0) sm.prof[PF_SOLVE] += clock64() - solve_t0;
@@ -464,8 +464,9 @@ static int launch_solve(cmpc_handle* h, int32_t batch, const double* x0, const d
   }
   const int grid = batch < h->slots ? batch : h->slots;
   // pass 0: as asked.  Retries (compact launches over the failed subset, usually empty: their CTAs exit at once): from
-  // the solver's cold start with initial barrier x 1 (only after a warm attempt), x 10, x 0.1
-  const double scale[4] = {1.0, 1.0, 10.0, 0.1};
+  // the solver's cold start with initial barrier x 1 (only after a warm attempt), x 10, and x 1 from another starting
+  // point (CoM states blended from x0 towards the reference along the horizon)
+  const double scale[4] = {1.0, 1.0, 10.0, 1.0};
   int prev = -1;                                      // index of the fail list the previous pass wrote
   for (int p = 0; p < 4; ++p) {
     if (p == 1 && warm_mode == CMPC_COLD) continue;   // a cold attempt with the same barrier value would repeat pass 0
@@ -477,7 +478,7 @@ static int launch_solve(cmpc_handle* h, int32_t batch, const double* x0, const d
     const int pnext = (p == 0 && warm_mode == CMPC_COLD) ? 2 : p + 1;
     int32_t* cout = last ? nullptr : h->d_queue + 4 + pnext;
     cmpc_solve_kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1, h->iter, h->istride,
-                                                              h->scratch, h->sstride, p == 0 ? warm_mode : CMPC_COLD, scale[p], p > 0, o, lin, cin, lout, cout,
+                                                              h->scratch, h->sstride, p == 0 ? warm_mode : CMPC_COLD, scale[p], p == 3, p > 0, o, lin, cin, lout, cout,
                                                               h->d_queue + p, h->d_last_iters, h->d_valid);
     CK(cudaGetLastError(), "cmpc_solve_kernel launch");
     ++nl; ++prev;

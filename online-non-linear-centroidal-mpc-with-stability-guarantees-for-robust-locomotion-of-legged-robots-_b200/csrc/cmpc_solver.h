@@ -24,6 +24,10 @@
 #define CMPC_HD_NOINLINE
 #endif
 
+#ifndef CMPC_SKIP_BLOCKS
+#define CMPC_SKIP_BLOCKS 1
+#endif
+
 namespace cmpc {
 
 constexpr int NW = 2;                       // multipliers kept as explicit unknowns per stage (Lyapunov row, angular-momentum row)
@@ -440,10 +444,11 @@ struct Solver {
   const Config& c; const Instance& in; Work w; Par& par;
   double mu, reg_last, mu_scale;
   int nfact, nreg;
+  bool start_blend;                           // cold start variant of the last retry
   int tile_i[Par::TPT], tile_j[Par::TPT];     // this thread's 4 x 4 register tiles of the stage block (row, column; -1 = none)
 
   CMPC_HD Solver(const Config& c_, const Instance& in_, const Work& w_, Smem& sm_, Par& par_)
-      : c(c_), in(in_), w(w_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0) { par.bind(&sm_); }
+      : c(c_), in(in_), w(w_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0), start_blend(false) { par.bind(&sm_); }
 
   // workspace sections, known to be global memory
   CMPC_HD double* gX() const { double* p = w.X; CMPC_ASSUME_GLOBAL(p); return p; }
@@ -475,8 +480,10 @@ struct Solver {
     if (warm == 0) {
       for (int t = tid; t < (N + 1) * NX; t += nt) {
         const int i = t / NX, j = t % NX;
-        gX()[t] = (j < NXP) ? i_x0()[j] : 0.0;
-        (void)i;
+        double v = (j < NXP) ? i_x0()[j] : 0.0;
+        // alternative start (last retry): CoM position / velocity blended from x0 towards the reference along the horizon
+        if (start_blend && i >= 1 && j < 6) { const double a = (double)i / (double)N; v = (1.0 - a) * v + a * i_com_ref()[9 * (i - 1) + j]; }
+        gX()[t] = v;
       }
       for (int t = tid; t < N * NU; t += nt) {
         const int i = t / NU, j = t % NU;
@@ -1202,6 +1209,29 @@ struct Solver {
             reinterpret_cast<Pair*>(pl)[2 * kk + 1] = Pair{t[8 + kk], t[12 + kk]};
           }
         };
+        // Blocks of four inputs that are DECOUPLED at this stage -- the forces of a swing foot (gamma = 0: no dynamics, no
+        // rows, cost 10 |f|^2 only, no force-rate term), the velocity / yaw-rate inputs in double support ((1 - gamma) = 0) -- have a diagonal
+        // block and nothing below it but the gradient row: their elimination step is the reciprocal root of the diagonal.
+        // Such a block takes no barrier, no panel and no update; its gradient-row entries are scaled when the tiles go back
+        // to shared memory.  Forces of the left / right foot are blocks 0-2 / 3-5, blocks 6-7 hold the foot inputs.
+        unsigned skipb = 0;
+#if CMPC_SKIP_BLOCKS
+        {
+          // (the force-rate term couples f_z of stage i to the state q with the PREVIOUS stage's gamma: the first swing stage
+          // after a lift-off is not decoupled)
+          const bool sl_ = R[Q_GAM] < 0.5 && R[Q_GAMP] == 0.0, sr_ = R[Q_GAM + 1] < 0.5 && R[Q_GAMP + 1] == 0.0;
+          const bool ds_ = R[Q_GAM] > 0.5 && R[Q_GAM + 1] > 0.5;
+          skipb = (sl_ ? 0x07u : 0u) | (sr_ ? 0x38u : 0u) | (ds_ ? 0xC0u : 0u);
+        }
+#endif
+        // diagonal tile of a decoupled block: L = sqrt(diag), reciprocal published for the gains
+        auto skip_diag = [&](double (&t)[16], int tk) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double dq = t[5 * q], iq = cmpc_rsqrt(dq);
+            sm.rdiag[4 * tk + q] = iq; t[5 * q] = dq * iq;
+          }
+        };
         {   // ---- block 0: tile column 0 (transient tiles)
           double C[Par::CPT][16];
           int ci_[Par::CPT];
@@ -1219,15 +1249,15 @@ struct Solver {
                   const int r = 4 * ci_[sl] + a_;
                   C[sl][4 * a_ + b_] = (r < MROWS && b_ <= r) ? sm.M[mi(r, b_)] : 0.0;
                 }
-              if (ci_[sl] == 0) mygood = diag_tile(C[sl], 0);
+              if (ci_[sl] == 0) { if (skipb & 1u) skip_diag(C[sl], 0); else mygood = diag_tile(C[sl], 0); }
             }
           }
-          if (!par.sync_and(mygood)) okp = false;                   // A: barrier + vote on the pivot test
+          if (!(skipb & 1u)) { if (!par.sync_and(mygood)) okp = false; }   // A: barrier + vote on the pivot test
           if (okp) {
 #pragma unroll
             for (int sl = 0; sl < Par::CPT; ++sl) {
               if (ci_[sl] < 0) continue;
-              if (ci_[sl] > 0) panel_tile(C[sl], ci_[sl]);
+              if (ci_[sl] > 0 && !(skipb & 1u)) panel_tile(C[sl], ci_[sl]);
 #pragma unroll
               for (int a_ = 0; a_ < 4; ++a_)
 #pragma unroll
@@ -1239,6 +1269,14 @@ struct Solver {
           }
         }
         for (int tk = 0; tk < NU / 4 && okp; ++tk) {
+          if ((skipb >> tk) & 1u) {                                 // decoupled block: diagonal only (uniform branch)
+            if (tk > 0) {
+#pragma unroll
+              for (int sl = 0; sl < Par::TPT; ++sl)
+                if (ti_[sl] == tk && tj_[sl] == tk) skip_diag(T[sl], tk);
+            }
+            continue;
+          }
           if (tk > 0) {
             bool mygood = true;
 #pragma unroll
@@ -1337,6 +1375,11 @@ struct Solver {
 #pragma unroll
         for (int sl = 0; sl < Par::TPT; ++sl) {
           if (ti_[sl] < 0) continue;
+          // gradient-row entries (row 62 = tile row 15, a_ = 2) of a decoupled block were left unscaled: L(62, c) = g_c / l_cc
+          if (ti_[sl] == 15 && tj_[sl] < NU / 4 && ((skipb >> tj_[sl]) & 1u)) {
+#pragma unroll
+            for (int b_ = 0; b_ < 4; ++b_) T[sl][8 + b_] *= sm.rdiag[4 * tj_[sl] + b_];
+          }
 #pragma unroll
           for (int a_ = 0; a_ < 4; ++a_)
 #pragma unroll
@@ -1345,6 +1388,7 @@ struct Solver {
               if (r < MROWS && cc <= r && cc < NZA) sm.M[mi(r, cc)] = T[sl][4 * a_ + b_];
             }
         }
+        if (skipb & 1u) for (int q = tid; q < 4; q += nt) sm.M[mi(GR, q)] *= sm.rdiag[q];   // same for block 0 (its tiles went back to shared memory earlier)
         par.sync();
       }
       CMPC_TOC(sm, PF_CHOL);
@@ -1355,6 +1399,7 @@ struct Solver {
         double v[NA];
 #pragma unroll
         for (int q = 0; q < NA; ++q) v[q] = -rowp[q];
+
 #pragma unroll
         for (int k = NA - 1; k >= 0; --k) {
           const double zk = v[k] * sm.rdiag[k];
@@ -1817,22 +1862,23 @@ struct Solver {
   }
 
   // one attempt (a launch pass of the CUDA path: the retries of failed instances are separate, compact launches there)
-  CMPC_HD void run_pass(int warm, double scale, Stats* st) {
+  CMPC_HD void run_pass(int warm, double scale, Stats* st, bool blend = false) {
     setup();
-    mu_scale = scale; mu = 0; reg_last = 0;
+    mu_scale = scale; mu = 0; reg_last = 0; start_blend = blend;
     run_once(warm, st);
   }
 
   // all attempts in sequence (host build of the core, tests/hostsim)
   CMPC_HD void run(int warm, Stats* st) {
     setup();
-    // attempts: as asked (warm or cold, mu_init) -> cold, mu_init -> cold, 10 mu_init -> cold, mu_init / 10
+    // attempts: as asked (warm or cold, mu_init) -> cold, mu_init -> cold, 10 mu_init -> cold from the reference-blended start, mu_init
     mu_scale = 1.0;
     run_once(warm, st);
     int it0 = st->iters;
     for (int attempt = (warm == 0 ? 1 : 0); attempt < 3; ++attempt) {
       if (st->status == ST_CONVERGED || st->status == ST_INFEASIBLE_X0) break;
-      mu_scale = (attempt == 0) ? 1.0 : (attempt == 1 ? 10.0 : 0.1);
+      mu_scale = (attempt == 0) ? 1.0 : (attempt == 1 ? 10.0 : 1.0);
+      start_blend = (attempt == 2);                                  // last attempt: another starting point instead of another barrier value
       par.sync();
       mu = 0; reg_last = 0;
       run_once(0, st);

@@ -47,3 +47,36 @@ def test_sampling_quirks(pkg):
     assert pos[5] == 0.5 + 0.5 ** 5 and acc[5] == 20 * 0.5 ** 3 / 4.0
     with pytest.raises(ValueError):
         sample_tables([4, 4], coeff)
+
+
+def test_compute_knot_restated_from_the_plan(pkg, walk):
+    """`compute_knot` (functions.py:11-56) restated on the plan alone reproduces the knots / segment ticks the reference's own
+    compute_knot produced with its foot trajectory generator (fixture made by importing the reference), and the whole
+    `references` chain reproduces the tables."""
+    from cmpc_b200.com_reference import compute_knot, references
+    plan = [{"pos": walk["plan_pos"][j], "ang": walk["plan_ang"][j], "ss_duration": int(walk["plan_ss"][j]), "ds_duration": int(walk["plan_ds"][j]),
+             "foot_id": "lfoot" if int(walk["plan_foot"][j]) == 0 else "rfoot"} for j in range(len(walk["plan_ss"]))]
+    initial = {"lfoot": {"pos": walk["lfoot0"]}, "rfoot": {"pos": walk["rfoot0"]}}
+    kx, ky, sx, sy = compute_knot(plan, initial)
+    assert list(sx) == list(walk["seq_x"]) and list(sy) == list(walk["seq_y"])
+    assert np.array_equal(np.array(kx), walk["knot_x"]) and np.array_equal(np.array(ky), walk["knot_y"])
+    ref = references(plan, initial)
+    for k in ("pos_x", "vel_y", "acc_x", "pos_z"):
+        assert np.abs(ref[k] - walk["ref_" + k]).max() <= 1e-11, k
+
+
+def test_feet_positions_restated(pkg, walk):
+    """x / y of `generate_feet_trajectories_at_time` against the reference's precomputed foot tables (code/Debug/Pos {L,R}foot
+    pre trj reproduce these bit-exactly): the contact tables hold the planned poses in stance."""
+    from cmpc_b200.com_reference import feet_xy_at
+    plan = [{"pos": walk["plan_pos"][j], "ang": walk["plan_ang"][j], "ss_duration": int(walk["plan_ss"][j]), "ds_duration": int(walk["plan_ds"][j]),
+             "foot_id": "lfoot" if int(walk["plan_foot"][j]) == 0 else "rfoot"} for j in range(len(walk["plan_ss"]))]
+    initial = {"lfoot": {"pos": walk["lfoot0"]}, "rfoot": {"pos": walk["rfoot0"]}}
+    f = feet_xy_at(plan, initial, 50)
+    assert f["lfoot"] == tuple(walk["lfoot0"][3:5]) and f["rfoot"] == tuple(walk["rfoot0"][3:5])
+    f = feet_xy_at(plan, initial, 285)                               # double support of step 1: support plan[1], landed plan[2]
+    sup = plan[1]["foot_id"]; sw = "lfoot" if sup == "rfoot" else "rfoot"
+    assert f[sup] == tuple(plan[1]["pos"][0:2]) and f[sw] == tuple(plan[2]["pos"][0:2])
+    f = feet_xy_at(plan, initial, 335)                               # mid swing of step 2: half way between plan[1] and plan[3]
+    sup = plan[2]["foot_id"]; sw = "lfoot" if sup == "rfoot" else "rfoot"
+    assert abs(f[sw][0] - 0.5 * (plan[1]["pos"][0] + plan[3]["pos"][0])) < 1e-12
