@@ -167,6 +167,24 @@ int cmpc_assemble_device(const cmpc_walk_tables* tb, int32_t device, int32_t bat
                          const double* com_vel, const double* hw, const double* theta, const double* yaw, const double* plan,
                          double* x0, double* com_ref, double* foot_ref, double* gamma, int32_t* err, void* stream);
 
+/* ---- batched dense QP of the whole-body inverse-dynamics step -----------------------------------
+ * Replaces `QPSolver.set_values / solve` (code/utils.py:40-92: CasADi Opti('conic') + OSQP) as used by
+ * `InverseDynamics.get_joint_torques` (code/inverse_dynamics.py:30-135), for `batch` independent QPs of one size:
+ *     min 1/2 x'H x + F'x   s.t.  A_eq x = b_eq,  A_in x <= b_in
+ *   H [B][n][n] (symmetric), F [B][n], A_eq [B][m_eq][n], b_eq [B][m_eq], A_in [B][m_in][n], b_in [B][m_in], row-major.
+ * n <= 96, m_eq <= 48, m_in <= 32 (the reference: n = 2 dofs + 12, m_eq = dofs, m_in = 16).  One CTA per QP, Mehrotra
+ * predictor-corrector interior point on the quasi-definite KKT matrix in shared memory, FP64; H + 1e-9 I (the
+ * reference's H is singular in the torque block, OSQP regularises likewise).  tol <= 0 -> 1e-9, max_iter <= 0 -> 60.
+ * Outputs: x [B][n], status [B] (0 converged, 1 max_iter, 3 bad pivot, 5 nan), iters [B] (either may be NULL).
+ * The reference returns zeros when OSQP fails (utils.py:85-92); here the caller decides from `status`. */
+int cmpc_qp_solve_device(int32_t device, int32_t batch, int32_t n, int32_t m_eq, int32_t m_in, const double* H, const double* F,
+                         const double* A_eq, const double* b_eq, const double* A_in, const double* b_in, double tol, int32_t max_iter,
+                         double* x, int32_t* status, int32_t* iters, void* stream);
+/* Same with HOST buffers (allocates device staging per call: a convenience path, not a hot path). */
+int cmpc_qp_solve_host(int32_t device, int32_t batch, int32_t n, int32_t m_eq, int32_t m_in, const double* H, const double* F,
+                       const double* A_eq, const double* b_eq, const double* A_in, const double* b_in, double tol, int32_t max_iter,
+                       double* x, int32_t* status, int32_t* iters);
+
 /* Peak-FP64 probe: runs a dependent-free DFMA loop on every SM and returns the measured TFLOP/s. */
 int cmpc_measure_fp64_peak(int32_t device, double* tflops);
 

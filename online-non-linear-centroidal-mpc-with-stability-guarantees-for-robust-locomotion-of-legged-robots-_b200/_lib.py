@@ -105,7 +105,7 @@ def load():
 
 EXPORTS = ["cmpc_default_config", "cmpc_create", "cmpc_destroy", "cmpc_last_error", "cmpc_version", "cmpc_solve_device",
            "cmpc_solve_host", "cmpc_solve_host_traj", "cmpc_get_trajectory", "cmpc_set_warm", "cmpc_reset_warm", "cmpc_warm_save", "cmpc_warm_restore", "cmpc_last_stats",
-           "cmpc_footprint", "cmpc_phase_cycles", "cmpc_measure_fp64_peak", "cmpc_assemble_device"]
+           "cmpc_footprint", "cmpc_phase_cycles", "cmpc_measure_fp64_peak", "cmpc_assemble_device", "cmpc_qp_solve_device", "cmpc_qp_solve_host"]
 
 
 def _check(L, rc, what):

@@ -11,6 +11,7 @@
 
 #include "../../include/cmpc.h"
 #include "cmpc_solver.h"
+#include "cmpc_qp.cuh"
 
 using namespace cmpc;
 
@@ -697,6 +698,56 @@ int cmpc_assemble_device(const cmpc_walk_tables* tb, int32_t device, int32_t bat
   cmpc_assemble_kernel<<<batch, 128, 0, (cudaStream_t)stream>>>(*tb, batch, tick, com_pos, com_vel, hw, theta, yaw, plan, x0, com_ref, foot_ref, gamma, err);
   CK(cudaGetLastError(), "cmpc_assemble_kernel launch");
   return 0;
+}
+
+// ---- batched dense QP of the whole-body inverse-dynamics step (csrc/cmpc_qp.cuh)
+int cmpc_qp_solve_device(int32_t device, int32_t batch, int32_t n, int32_t m_eq, int32_t m_in, const double* H, const double* F,
+                         const double* A_eq, const double* b_eq, const double* A_in, const double* b_in, double tol, int32_t max_iter,
+                         double* x, int32_t* status, int32_t* iters, void* stream) {
+  using namespace cmpc_qp;
+  if (batch < 1 || n < 1 || n > QP_MAXN || m_eq < 0 || m_eq > QP_MAXE || m_in < 0 || m_in > QP_MAXI)
+    return fail(-1, "cmpc_qp_solve_device: bad sizes (n <= 96, m_eq <= 48, m_in <= 32)");
+  if (!H || !F || !x || (m_eq && (!A_eq || !b_eq)) || (m_in && (!A_in || !b_in))) return fail(-1, "cmpc_qp_solve_device: null pointer");
+  CK(cudaSetDevice(device), "cudaSetDevice");
+  QpDims d{n, m_eq, m_in, max_iter > 0 ? max_iter : 60, tol > 0 ? tol : 1e-9, 1e-9, 1e-11};
+  const size_t smem = qp_smem_doubles(n, m_eq, m_in) * sizeof(double);
+  CK(cudaFuncSetAttribute(cmpc_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(qp smem)");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmpc_qp_kernel, QP_THREADS, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (per_sm < 1) return fail(-1, "cmpc_qp_solve_device: the QP does not fit in shared memory");
+  const int slots = per_sm * prop.multiProcessorCount;
+  cmpc_qp_kernel<<<batch < slots ? batch : slots, QP_THREADS, smem, (cudaStream_t)stream>>>(d, batch, H, F, A_eq, b_eq, A_in, b_in, x, status, iters);
+  CK(cudaGetLastError(), "cmpc_qp_kernel launch");
+  return 0;
+}
+
+int cmpc_qp_solve_host(int32_t device, int32_t batch, int32_t n, int32_t m_eq, int32_t m_in, const double* H, const double* F,
+                       const double* A_eq, const double* b_eq, const double* A_in, const double* b_in, double tol, int32_t max_iter,
+                       double* x, int32_t* status, int32_t* iters) {
+  if (batch < 1 || n < 1 || !H || !F || !x) return fail(-1, "cmpc_qp_solve_host: bad arguments");
+  CK(cudaSetDevice(device), "cudaSetDevice");
+  const size_t B = (size_t)batch;
+  const size_t sz[6] = {B * n * n, B * n, B * m_eq * n, B * m_eq, B * m_in * n, B * m_in};
+  const double* src[6] = {H, F, A_eq, b_eq, A_in, b_in};
+  size_t tot = 0; for (int k = 0; k < 6; ++k) tot += sz[k];
+  double* dbuf = nullptr; int32_t* ibuf = nullptr;
+  CK(cudaMalloc(&dbuf, (tot + B * n) * sizeof(double)), "cudaMalloc(qp)");
+  if (cudaMalloc(&ibuf, 2 * B * sizeof(int32_t)) != cudaSuccess) { cudaFree(dbuf); return fail(-2, "cudaMalloc(qp status)"); }
+  double* dp[6]; size_t off = 0;
+  int rc = 0;
+  for (int k = 0; k < 6 && !rc; ++k) {
+    dp[k] = dbuf + off; off += sz[k];
+    if (sz[k] && cudaMemcpy(dp[k], src[k], sz[k] * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(-2, "cmpc_qp_solve_host: H2D");
+  }
+  double* dx = dbuf + tot;
+  if (!rc) rc = cmpc_qp_solve_device(device, batch, n, m_eq, m_in, dp[0], dp[1], dp[2], dp[3], dp[4], dp[5], tol, max_iter, dx, ibuf, ibuf + B, nullptr);
+  if (!rc && cudaMemcpy(x, dx, B * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-2, "cmpc_qp_solve_host: kernel execution / D2H");
+  if (!rc && status && cudaMemcpy(status, ibuf, B * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-2, "cmpc_qp_solve_host: D2H");
+  if (!rc && iters && cudaMemcpy(iters, ibuf + B, B * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(-2, "cmpc_qp_solve_host: D2H");
+  cudaFree(dbuf); cudaFree(ibuf);
+  return rc;
 }
 
 int cmpc_measure_fp64_peak(int32_t device, double* tflops) {
