@@ -258,7 +258,7 @@ def main():
     config = {"workload": workload, "baseline_config": a.config, "batch_per_gpu": B, "horizon": N,
               "warm_start": ("mode %d (4 = per instance: shifted while a landing is inside the horizon, else full), device snapshot of tick t-1 restored every step" % WM)
                             if warm_replay else "cold (solver's own initial guess)",
-              "launches_per_step": "memset + cmpc_order_kernel (launch order from tick t-1's work; warm only) + cmpc_solve_kernel + up to 3 compact retry launches of the failed subset",
+              "launches_per_step": "cmpc_order_kernel (launch order from tick t-1's work; warm only) + cmpc_solve_kernel (persistent CTAs, retries of failed instances re-enter its work queue); two small memsets",
               "cache": "%s", "parallelism": "instances sharded over %d GPU(s), no collective on the hot path" % world}
 
     # ------------------------------------------------------------------ reference arm: restated CPU path only
@@ -300,7 +300,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     t = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)
     over = {k: float(v) for k, v in (kv.split("=") for kv in a.cfg)}
-    for k in ("max_iter", "ls_max", "stall_window"):
+    for k in ("max_iter", "ls_max", "stall_window", "stall_final"):
         if k in over:
             over[k] = int(over[k])
     R = 0 if (a.no_extras or a.config != 2) else max(K, 1)           # ticks ahead for the rolling replay
@@ -370,7 +370,7 @@ def main():
     status = out["status"].cpu().numpy()
     conv = int((status == 0).sum())
     st = solver.last_stats()                                            # last step's kernels (all steps are identical work)
-    launches_per_step = st["launches"] + 1                              # + the work-queue memset
+    launches_per_step = st["launches"]                                  # kernels (the two queue memsets are not kernels)
     # per-kernel duration of a step, measured live with CUDA events on the launching stream
     kms = []
     for _ in range(min(K, 3)):

@@ -60,7 +60,7 @@ typedef struct cmpc_config {
   int32_t ls_max;         /* backtracking steps of the filter line search */
   int32_t threads;        /* threads per instance (CTA size): 128 */
   int32_t stall_window;   /* an attempt whose barrier-problem error has not halved in this many iterations is abandoned (0 = off) */
-  int32_t reserved0;
+  int32_t stall_final;    /* the same at the final barrier value (a healthy end game takes 2-4 iterations) */
   double delta;           /* world_time_step * mpc_rate (:11) */
   double grav;            /* params['g'] (:18) */
   double mu_fric;         /* 0.5 (:41) */
@@ -96,9 +96,10 @@ const char* cmpc_version(void);
  * Asynchronous on `stream` (a cudaStream_t).  stream == NULL means the handle's own non-blocking stream, NOT the CUDA
  * default stream.  Every operation on a handle is ordered after the previous operation on that handle, whatever streams
  * the two were issued on (the handle records an event behind each operation and later operations wait for it).
- * The warm-start state lives in the handle.  Instances that do not converge are solved again by up to three compact
- * follow-up launches (cold start; then a ten times larger initial barrier value; then another starting point, CoM states blended
- * towards the reference along the horizon); `iters` accumulates over the attempts. */
+ * The warm-start state lives in the handle.  An instance that does not converge is solved again inside the same launch
+ * (it re-enters the work queue of the persistent CTAs): from the solver's cold start; then with a ten times larger initial
+ * barrier value; then from another starting point, CoM states blended towards the reference along the horizon; `iters`
+ * accumulates over the attempts. */
 int cmpc_solve_device(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref,
                       const double* foot_ref, const double* gamma, const double* mass, const double* k1,
                       int32_t warm_mode, double* x1, double* u0, double* xN, double* cost, double* viol,

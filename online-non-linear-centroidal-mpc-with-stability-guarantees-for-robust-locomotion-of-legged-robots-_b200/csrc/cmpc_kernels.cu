@@ -85,34 +85,59 @@ struct Outputs {
   unsigned long long* prof;   // [PF_COUNT] phase cycles summed over CTAs (only with -DCMPC_PROFILE)
 };
 
-// One launch = one PASS over a list of instances.  Persistent CTAs (one per resident slot: SMs x CTAs per SM) pull
-// instances from an atomic work counter in list order; the scratch (Newton step, derivative records, stage factors)
-// belongs to the CTA slot, only the iterate belongs to the instance.  Pass 0 solves every instance as asked (warm or
-// cold); an instance that does not converge is appended to `list_out` and solved again by the next pass from the
-// solver's own cold start with another initial barrier value (mu_scale) or starting point (blend) -- a second, compact launch over the failed
-// subset instead of a retry loop inside the CTA, which left every other slot waiting for the few long ones.
+// One launch solves a tick of the whole batch, retries included.  Persistent CTAs (one per resident slot: SMs x CTAs per
+// SM) pull work from a queue in global memory: first the instances in launch order (atomic cursor `next`), then the retry
+// ring.  The scratch (Newton step, derivative records, stage factors) belongs to the CTA slot, only the iterate belongs
+// to the instance.  An instance whose attempt does not converge is appended to the ring with its next attempt -- the
+// solver's own cold start (only after a warm attempt), then a ten times larger initial barrier value, then another
+// starting point (CoM states blended from x0 towards the reference) -- and is picked up by the next free slot: the
+// retries of the few hard instances overlap with the tail of the batch instead of running behind it.  A CTA that finds
+// no work waits (nanosleep polling) until every instance is resolved, because a running attempt may still queue a retry.
+struct Queue { int32_t next, head, tail, done; };      // cursor of the initial list; retry ring head / tail; resolved instances
+
+__device__ __forceinline__ int32_t ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+
 __global__ void __launch_bounds__(CMPC_THREADS, CMPC_MIN_CTAS)
 cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const double* __restrict__ com_ref,
                   const double* __restrict__ foot_ref, const double* __restrict__ gamma,
                   const double* __restrict__ mass, const double* __restrict__ k1, double* iter, size_t istride,
-                  double* scratch, size_t sstride, int warm, double mu_scale, int blend, int accumulate, Outputs out,
-                  const int32_t* __restrict__ list_in, const int32_t* __restrict__ count_in, int32_t* __restrict__ list_out,
-                  int32_t* count_out, int32_t* next, int32_t* __restrict__ last_iters, int32_t* __restrict__ valid) {
+                  double* scratch, size_t sstride, int warm, Outputs out, const int32_t* __restrict__ order, Queue* q, int32_t* ring,
+                  int32_t* __restrict__ last_iters, int32_t* __restrict__ valid) {
   Smem& sm = *reinterpret_cast<Smem*>(cmpc_smem_raw);
   const int N = c.N;
-  const int n = count_in ? *count_in : batch;
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0) for (int k = 0; k < PF_COUNT; ++k) sm.prof[k] = 0;
   const long long cta_t0 = clock64();
 #endif
   double* my_scratch = scratch + sstride * blockIdx.x;
   for (;;) {
-    if (threadIdx.x == 0) sm.flag = atomicAdd(next, 1);
+    if (threadIdx.x == 0) {
+      int item = -1;
+      const int i = ld_volatile(&q->next) < batch ? atomicAdd(&q->next, 1) : batch;
+      if (i < batch) item = order ? order[i] : i;                 // attempt 0, longest-expected-first order (cmpc_order_kernel)
+      else {
+        const long long t0 = clock64();
+        for (;;) {
+          const int h = ld_volatile(&q->head), t = ld_volatile(&q->tail);
+          if (h < t) {
+            if (atomicCAS(&q->head, h, h + 1) != h) continue;     // another slot took it
+            int e;
+            while ((e = ld_volatile(ring + h)) < 0) { }           // (the producer publishes the entry right after reserving it)
+            item = e;
+            break;
+          }
+          if (ld_volatile(&q->done) >= batch) break;              // every instance resolved: no retry can appear any more
+          __nanosleep(2000);
+          if (clock64() - t0 > 40000000000ll) break;              // safety net (~20 s): never hang the device
+        }
+      }
+      sm.flag = item;
+    }
     __syncthreads();
-    const int slot = sm.flag;
+    const int item = sm.flag;
     __syncthreads();
-    if (slot >= n) break;
-    const int b = list_in ? list_in[slot] : slot;    // pass 0: longest-expected-first order (cmpc_order_kernel); retries: the failed subset
+    if (item < 0) break;
+    const int b = item & 0x0fffffff, attempt = (item >> 28) & 7;
     Instance in;
     in.x0 = x0 + (size_t)NXP * b;
     in.com_ref = com_ref + (size_t)9 * N * b;
@@ -121,22 +146,29 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
     in.mass = mass[b];
     in.k1 = k1[b];
     Work w = carve_work(iter + istride * b, my_scratch, N);
-    const int wm = (warm != 0 && valid && !valid[b]) ? 0 : warm;      // no previous solution of this instance: cold
+    int wm = 0;
+    if (attempt == 0) wm = (warm != 0 && valid && !valid[b]) ? 0 : warm;        // no previous solution of this instance: cold
     ParCta par;
     Solver<ParCta> sol(c, in, w, sm, par);
     Stats st;
 #ifdef CMPC_PROFILE
     const long long solve_t0 = clock64();
 #endif
-    sol.run_pass(wm, mu_scale, &st, blend != 0);
+    sol.run_pass(wm, attempt == 2 ? 10.0 : 1.0, &st, attempt == 3);
     __syncthreads();
 #ifdef CMPC_PROFILE
     if (threadIdx.x == 0) sm.prof[PF_SOLVE] += clock64() - solve_t0;
 #endif
     const int tid = threadIdx.x;
-    if (out.x1) for (int j = tid; j < NXP; j += blockDim.x) out.x1[(size_t)NXP * b + j] = w.X[NX + j];
-    if (out.xN) for (int j = tid; j < NXP; j += blockDim.x) out.xN[(size_t)NXP * b + j] = w.X[N * NX + j];
-    if (out.u0) for (int j = tid; j < NU; j += blockDim.x) out.u0[(size_t)NU * b + j] = w.U[j];
+    const bool failed = st.status != ST_CONVERGED && st.status != ST_INFEASIBLE_X0;
+    const int next_attempt = (attempt == 0) ? (wm != 0 ? 1 : 2) : attempt + 1;
+    const bool retry = failed && next_attempt <= 3;
+    const bool accumulate = attempt > 0;
+    if (!retry) {
+      if (out.x1) for (int j = tid; j < NXP; j += blockDim.x) out.x1[(size_t)NXP * b + j] = w.X[NX + j];
+      if (out.xN) for (int j = tid; j < NXP; j += blockDim.x) out.xN[(size_t)NXP * b + j] = w.X[N * NX + j];
+      if (out.u0) for (int j = tid; j < NU; j += blockDim.x) out.u0[(size_t)NU * b + j] = w.U[j];
+    }
     if (tid == 0) {
       if (out.cost) out.cost[b] = st.cost;
       if (out.viol) out.viol[b] = st.viol;
@@ -148,9 +180,13 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
       }
       if (last_iters) last_iters[b] = (accumulate ? last_iters[b] : 0) + st.nfact;
       if (valid) valid[b] = 1;
-      if (list_out && st.status != ST_CONVERGED && st.status != ST_INFEASIBLE_X0) list_out[atomicAdd(count_out, 1)] = b;
     }
     __syncthreads();
+    if (tid == 0) {
+      __threadfence();                                            // this attempt's writes are visible before the instance is handed on / counted
+      if (retry) { const int slot = atomicAdd(&q->tail, 1); ring[slot] = b | (next_attempt << 28); __threadfence(); }
+      else atomicAdd(&q->done, 1);
+    }
   }
 #ifdef CMPC_PROFILE
   if (threadIdx.x == 0) sm.prof[PF_CTA] = clock64() - cta_t0;
@@ -287,8 +323,8 @@ struct cmpc_handle {
   int32_t* d_counters; int32_t* h_counters;
   int32_t* d_last_iters; int32_t* d_perm;     // work of the previous solve per instance, launch order of the next one
   int32_t* d_valid;                           // per instance: a previous solution exists (warm start possible)
-  int32_t* d_queue;                           // [0..3] work counters of the passes, [4..7] lengths of the retry lists
-  int32_t* d_fail;                            // [3][cap] instances to retry
+  int32_t* d_queue;                           // work queue of a launch (struct Queue)
+  int32_t* d_fail;                            // [3 cap] retry ring: instance | attempt << 28
   uint8_t* d_mask;                            // staging of cmpc_reset_warm's mask
   double* d_traj; double* h_traj; size_t traj_cap;   // trajectory staging (allocated at first use, kept)
   unsigned long long* d_prof;
@@ -336,7 +372,7 @@ int cmpc_default_config(int32_t N, cmpc_config* cfg) {
   if (!cfg || N < 1 || N > NMAX) return fail(-1, "cmpc_default_config: bad arguments (1 <= N <= 64)");
   Config c = default_config(N);
   memset(cfg, 0, sizeof(*cfg));
-  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS; cfg->stall_window = c.stall_window;
+  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS; cfg->stall_window = c.stall_window; cfg->stall_final = c.stall_final;
   cfg->delta = c.delta; cfg->grav = c.grav; cfg->mu_fric = c.mu_fric;
   cfg->foot_half_len = c.hl; cfg->foot_half_wid = c.hw;
   cfg->w_h = c.w_h; cfg->w_xy = c.w_xy; cfg->w_zc = c.w_zc; cfg->w_foot = c.w_foot; cfg->w_sym = c.w_sym;
@@ -350,7 +386,7 @@ int cmpc_default_config(int32_t N, cmpc_config* cfg) {
 
 static Config to_internal(const cmpc_config* u) {
   Config c = default_config(u->N);
-  c.max_iter = u->max_iter; c.ls_max = u->ls_max; c.stall_window = u->stall_window;
+  c.max_iter = u->max_iter; c.ls_max = u->ls_max; c.stall_window = u->stall_window; c.stall_final = u->stall_final;
   c.delta = u->delta; c.grav = u->grav; c.mu_fric = u->mu_fric;
   c.hl = u->foot_half_len; c.hw = u->foot_half_wid; c.w_h = u->w_h; c.w_xy = u->w_xy; c.w_zc = u->w_zc;
   c.w_foot = u->w_foot; c.w_sym = u->w_sym; c.w_swing = u->w_swing; c.w_rate = u->w_rate; c.eps_reg = u->eps_reg;
@@ -454,37 +490,21 @@ int cmpc_destroy(cmpc_handle* h) {
 // the launches of one solve on stream s (no ordering / bookkeeping)
 static int launch_solve(cmpc_handle* h, int32_t batch, const double* x0, const double* com_ref, const double* foot_ref, const double* gamma,
                         const double* mass, const double* k1, int32_t warm_mode, const Outputs& o, cudaStream_t s, int* launches) {
-  const size_t B = (size_t)h->cap;
   CK(cudaMemsetAsync(h->d_queue, 0, 8 * sizeof(int32_t), s), "memset queue");
-  const int32_t* list = nullptr;
+  CK(cudaMemsetAsync(h->d_fail, 0xFF, 3 * (size_t)batch * sizeof(int32_t), s), "memset retry ring");     // -1: entry not published yet
+  const int32_t* order = nullptr;
   int nl = 0;
   if (warm_mode != CMPC_COLD) {                       // the previous solve of these instances tells how expensive they are
     cmpc_order_kernel<<<1, 1024, 0, s>>>(batch, h->cfg.N, h->d_last_iters, gamma, h->d_perm);
     CK(cudaGetLastError(), "cmpc_order_kernel launch");
-    list = h->d_perm; ++nl;
+    order = h->d_perm; ++nl;
   }
   const int grid = batch < h->slots ? batch : h->slots;
-  // pass 0: as asked.  Retries (compact launches over the failed subset, usually empty: their CTAs exit at once): from
-  // the solver's cold start with initial barrier x 1 (only after a warm attempt), x 10, and x 1 from another starting
-  // point (CoM states blended from x0 towards the reference along the horizon)
-  const double scale[4] = {1.0, 1.0, 10.0, 1.0};
-  int prev = -1;                                      // index of the fail list the previous pass wrote
-  for (int p = 0; p < 4; ++p) {
-    if (p == 1 && warm_mode == CMPC_COLD) continue;   // a cold attempt with the same barrier value would repeat pass 0
-    const bool last = (p == 3);
-    const int32_t* lin = (p == 0) ? list : h->d_fail + (size_t)prev * B;
-    const int32_t* cin = (p == 0) ? nullptr : h->d_queue + 4 + p;
-    int32_t* lout = last ? nullptr : h->d_fail + (size_t)(prev + 1) * B;
-    // the next LAUNCHED pass reads its count from d_queue[4 + its index]
-    const int pnext = (p == 0 && warm_mode == CMPC_COLD) ? 2 : p + 1;
-    int32_t* cout = last ? nullptr : h->d_queue + 4 + pnext;
-    cmpc_solve_kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1, h->iter, h->istride,
-                                                              h->scratch, h->sstride, p == 0 ? warm_mode : CMPC_COLD, scale[p], p == 3, p > 0, o, lin, cin, lout, cout,
-                                                              h->d_queue + p, h->d_last_iters, h->d_valid);
-    CK(cudaGetLastError(), "cmpc_solve_kernel launch");
-    ++nl; ++prev;
-  }
-  *launches = nl;
+  cmpc_solve_kernel<<<grid, h->threads, h->smem_bytes, s>>>(h->cfg, batch, x0, com_ref, foot_ref, gamma, mass, k1, h->iter, h->istride,
+                                                            h->scratch, h->sstride, warm_mode, o, order, reinterpret_cast<Queue*>(h->d_queue), h->d_fail,
+                                                            h->d_last_iters, h->d_valid);
+  CK(cudaGetLastError(), "cmpc_solve_kernel launch");
+  *launches = nl + 1;
   return 0;
 }
 

@@ -57,6 +57,7 @@ struct Config {
   double warm_push, warm_comp;      // full warm start: slack floor, and cap on s*lam/mu_warm (0 = none)
   int max_iter, ls_max;
   int stall_window;                 // iterations without halving the barrier-problem error before an attempt is abandoned (0 = off)
+  int stall_final;                  // the same at the final barrier value
   double xp[8];                     // experiment knobs (studies with the tests/hostsim build)
 };
 
@@ -71,7 +72,7 @@ CMPC_HD Config default_config(int N) {
   c.mu_init = 0.1; c.mu_final = 1e-9; c.tol = 1e-8; c.kappa_eps = 10.0; c.kappa_mu = 0.2;
   c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 1e-6; c.warm_comp = 0.0;
   for (int j = 0; j < 8; ++j) c.xp[j] = 0.0;
-  c.stall_window = 60;
+  c.stall_window = 60; c.stall_final = 20;
   c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
   return c;
 }

@@ -1142,6 +1142,21 @@ struct Solver {
       // The two explicit multipliers (columns 32, 33; pivot sign -1) follow column by column.  The gradient row
       // (row 62) is carried along.  Inputs without coupling at a stage (stance-foot velocities, swing-foot
       // tangential forces) need no special case: their columns are zero below the diagonal.
+      // Blocks of four inputs that are DECOUPLED at this stage -- the forces of a swing foot (gamma = 0: no dynamics, no
+      // rows, cost 10 |f|^2 only, no force-rate term), the velocity / yaw-rate inputs in double support ((1 - gamma) = 0) -- have a diagonal
+      // block and nothing below it but the gradient row: their elimination step is the reciprocal root of the diagonal.
+      // Such a block takes no barrier, no panel and no update; its gradient-row entries are scaled when the tiles go back
+      // to shared memory.  Forces of the left / right foot are blocks 0-2 / 3-5, blocks 6-7 hold the foot inputs.
+      unsigned skipb = 0;
+#if CMPC_SKIP_BLOCKS
+      {
+        // (the force-rate term couples f_z of stage i to the state q with the PREVIOUS stage's gamma: the first swing stage
+        // after a lift-off is not decoupled)
+        const bool sl_ = R[Q_GAM] < 0.5 && R[Q_GAMP] == 0.0, sr_ = R[Q_GAM + 1] < 0.5 && R[Q_GAMP + 1] == 0.0;
+        const bool ds_ = R[Q_GAM] > 0.5 && R[Q_GAM + 1] > 0.5;
+        skipb = (sl_ ? 0x07u : 0u) | (sr_ ? 0x38u : 0u) | (ds_ ? 0xC0u : 0u);
+      }
+#endif
       {
         double T[Par::TPT][16];
         int ti_[Par::TPT], tj_[Par::TPT];
@@ -1209,21 +1224,6 @@ struct Solver {
             reinterpret_cast<Pair*>(pl)[2 * kk + 1] = Pair{t[8 + kk], t[12 + kk]};
           }
         };
-        // Blocks of four inputs that are DECOUPLED at this stage -- the forces of a swing foot (gamma = 0: no dynamics, no
-        // rows, cost 10 |f|^2 only, no force-rate term), the velocity / yaw-rate inputs in double support ((1 - gamma) = 0) -- have a diagonal
-        // block and nothing below it but the gradient row: their elimination step is the reciprocal root of the diagonal.
-        // Such a block takes no barrier, no panel and no update; its gradient-row entries are scaled when the tiles go back
-        // to shared memory.  Forces of the left / right foot are blocks 0-2 / 3-5, blocks 6-7 hold the foot inputs.
-        unsigned skipb = 0;
-#if CMPC_SKIP_BLOCKS
-        {
-          // (the force-rate term couples f_z of stage i to the state q with the PREVIOUS stage's gamma: the first swing stage
-          // after a lift-off is not decoupled)
-          const bool sl_ = R[Q_GAM] < 0.5 && R[Q_GAMP] == 0.0, sr_ = R[Q_GAM + 1] < 0.5 && R[Q_GAMP + 1] == 0.0;
-          const bool ds_ = R[Q_GAM] > 0.5 && R[Q_GAM + 1] > 0.5;
-          skipb = (sl_ ? 0x07u : 0u) | (sr_ ? 0x38u : 0u) | (ds_ ? 0xC0u : 0u);
-        }
-#endif
         // diagonal tile of a decoupled block: L = sqrt(diag), reciprocal published for the gains
         auto skip_diag = [&](double (&t)[16], int tk) {
 #pragma unroll
@@ -1928,13 +1928,15 @@ struct Solver {
         stall_it = it; stall_ref = -1.0;
       }
       // stall test: an attempt whose barrier-problem error has not halved within `stall_window` iterations at one barrier
-      // value is abandoned (it would run to max_iter: jammed at a saddle of the non-convex NLP, or diverging); the caller
+      // value (`stall_final` at the last one: a healthy end game takes two to four iterations, an attempt parked at a
+      // saddle of the non-convex NLP -- primal feasible, complementary, dual residual stuck, regularisation at every
+      // iteration -- never leaves it) is abandoned (it would run to max_iter: jammed at a saddle of the non-convex NLP, or diverging); the caller
       // retries from another start
       if (c.stall_window > 0) {
         double p2[3];
         const double emu = kkt_error(ev, mu, nrows, p2);
         if (stall_ref < 0.0) { stall_ref = emu; stall_it = it; }
-        else if (it - stall_it >= c.stall_window) {
+        else if (it - stall_it >= (mu <= c.mu_final ? c.stall_final : c.stall_window)) {
           if (emu > 0.5 * stall_ref) { status = ST_STALL; break; }
           stall_ref = emu; stall_it = it;
         }

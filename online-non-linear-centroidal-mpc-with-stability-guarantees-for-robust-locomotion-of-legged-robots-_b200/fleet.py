@@ -22,9 +22,12 @@ from .assembly import PlanTables, ReferenceTables
 
 class Fleet:
     def __init__(self, batch, footstep_planner, params, CoM_ref, initial, hw_trace=None, device=0, k1=None, mass=None,
-                 tick_offset=None, warm_mode=WARM_AUTO, **solver_overrides):
+                 tick_offset=None, warm_mode=WARM_AUTO, plant_mass=None, **solver_overrides):
         """tick_offset: optional int array [B]: robot b is at tick t + tick_offset[b] when the fleet is stepped at tick t
-        (robots at different phases of the same walk in one batch)."""
+        (robots at different phases of the same walk in one batch).
+        plant_mass: optional [B] true masses of the simulated robots (BASELINE config 4 (ii): the MPC keeps `mass`, the plant
+        carries a payload): the CoM is then integrated from the applied contact forces, p+ = p + d v, v+ = v + d (g + F / m_plant),
+        instead of being set to the MPC's own prediction, and theta_hat has something to estimate."""
         import torch
         self.torch = torch
         self.B, self.N = int(batch), int(params["N"])
@@ -46,6 +49,8 @@ class Fleet:
         self.solver = BatchSolver(self.N, self.B, device=device, delta=delta, grav=params["g"], w_rate=0.0 if self.rate == 10 else 1.0,
                                   **solver_overrides)
         self.warm_mode = warm_mode
+        self.plant_mass = None if plant_mass is None else torch.as_tensor(np.asarray(plant_mass, float), **f64).contiguous()
+        self.delta = delta
         rep = lambda v: torch.as_tensor(np.asarray(v, float), **f64).repeat(self.B, 1).contiguous()
         self.com_pos, self.com_vel = rep(initial["com"]["pos"]), rep(initial["com"]["vel"])
         self.hw = rep(initial["hw"]["val"])
@@ -85,8 +90,16 @@ class Fleet:
         self.alive &= ok                                       # a failed solve is where the reference would crash (:605-614)
         x1, u0, xN = out["x1"], out["u0"], out["xN"]
         upd = self.alive.unsqueeze(1)
-        self.com_pos = torch.where(upd, x1[:, 0:3], self.com_pos)
-        self.com_vel = torch.where(upd, x1[:, 3:6], self.com_vel)
+        if self.plant_mass is None:                            # surrogate plant of DESIGN.md section 3: the model itself
+            new_pos, new_vel = x1[:, 0:3], x1[:, 3:6]
+        else:                                                  # a plant of another mass under the applied forces (Euler step, :187-190)
+            g0 = gamma[:, 0]
+            F = g0[:, 0:1] * u0[:, 0:12].reshape(-1, 4, 3).sum(1) + g0[:, 1:2] * u0[:, 12:24].reshape(-1, 4, 3).sum(1)
+            acc = F / self.plant_mass.unsqueeze(1)
+            acc[:, 2] -= self.g
+            new_pos, new_vel = self.com_pos + self.delta * self.com_vel, self.com_vel + self.delta * acc
+        self.com_pos = torch.where(upd, new_pos, self.com_pos)
+        self.com_vel = torch.where(upd, new_vel, self.com_vel)
         self.theta = torch.where(upd, x1[:, 9:12], self.theta)
         self.yaw = torch.where(upd, torch.stack([x1[:, 12], x1[:, 16]], 1), self.yaw)
         if self.hw_trace is not None:

@@ -5,7 +5,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 TAG=${1:-r02}
 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/plain_dram_$TAG.log 2>&1 || exit 1
-# launches of the solve kernel in that command: 2 setup solves x 3-4 passes, then (warm-up, timed, 1 kernel-time repeat, 3 e2e) steps of 4 passes
+# launches of the solve kernel in that command: 2 setup solves, then one launch per step (warm-up, timed, kernel-time repeat, e2e warm-up, e2e)
 timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:cmpc_solve_kernel --csv \
     --log-file gpurun_out/dram_bytes_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/ncu_dram_$TAG.log 2>&1
 python - "$TAG" <<'PY'
@@ -26,8 +26,8 @@ for i in sorted(by):
     rd = m["dram__bytes_read.sum"][0] * scale[m["dram__bytes_read.sum"][1]]
     wr = m["dram__bytes_write.sum"][0] * scale[m["dram__bytes_write.sum"][1]]
     launch.append((rd, wr, m["gpu__time_duration.sum"][0]))
-# setup: tick t-2 cold (3 passes), tick t-1 warm (4 passes); every step after that is 4 passes (pass 0 + 3 retry launches)
-steps = [launch[7 + 4 * k: 11 + 4 * k] for k in range((len(launch) - 7) // 4)]
+# setup: tick t-2 cold, tick t-1 warm; every launch after that is one step
+steps = [launch[2 + k: 3 + k] for k in range(len(launch) - 2)]
 per_step = [sum(a + b for a, b, _ in s) for s in steps]
 out = {"config": 2, "batch": 4096, "horizon": 20, "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, -k cmpc_solve_kernel, bench.py --steps 1 --warmup 1 (%s)" % tag,
        "launches": len(launch), "dram_bytes_per_step_all": per_step, "dram_bytes_per_step": sorted(per_step)[len(per_step) // 2] if per_step else None,

@@ -1,4 +1,4 @@
 cd "$GRAFT_REPO_ROOT"
-echo "### A/B skip"; bash scripts/ab.sh lib/variants/lib_noskip.so lib/libcmpc_b200.so lib/variants/lib_noskip.so lib/libcmpc_b200.so
-echo "### profile"; CMPC_LIB=$PWD/lib/variants/lib_prof.so python scripts/phase_profile.py 20 4096 | tail -1
-echo "### tests"; timeout 1500 python -m pytest tests -x -q -m gpu -k "golden or parity" 2>&1 | tail -4
+echo "### tests"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+echo "### rolling"; timeout 300 python scripts/rolling_probe.py 4 | head -11
+echo "### bench"; timeout 300 bash scripts/ab.sh lib/libcmpc_b200.so

@@ -12,7 +12,7 @@ if [ "$2" == "ncu" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
       python bench.py --steps 1 --warmup 1 --batch 1024 --no-cpu-baseline --no-extras > gpurun_out/ncu_launch_$TAG.log 2>&1
   timeout 300 python bench.py --steps 1 --warmup 1 --batch 444 --no-cpu-baseline --no-extras > gpurun_out/plain2_$TAG.log 2>&1 &&
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:cmpc_solve_kernel -s 8 -c 1 -f -o gpurun_out/prof_$TAG \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:cmpc_solve_kernel -s 3 -c 1 -f -o gpurun_out/prof_$TAG \
       python bench.py --steps 1 --warmup 1 --batch 444 --no-cpu-baseline --no-extras > gpurun_out/ncu_full_$TAG.log 2>&1
   ncu -i gpurun_out/prof_$TAG.ncu-rep --page details > gpurun_out/prof_${TAG}_details.txt 2>&1
   ls -la gpurun_out/

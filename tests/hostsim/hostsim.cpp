@@ -149,6 +149,7 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[13] == cfg_over[13]) c.warm_push = cfg_over[13];
     if (cfg_over[14] == cfg_over[14]) c.warm_comp = cfg_over[14];
     if (cfg_over[23] == cfg_over[23]) c.stall_window = (int)cfg_over[23];
+    if (cfg_over[24] == cfg_over[24]) c.stall_final = (int)cfg_over[24];
     for (int j = 0; j < 8; ++j) if (cfg_over[15 + j] == cfg_over[15 + j]) c.xp[j] = cfg_over[15 + j];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};

@@ -116,3 +116,28 @@ def test_fleet_against_the_oracle_driven_loop(pkg):
     for b in range(len(offs)):
         assert np.abs(traj[:, b] - refs[b][:, 0:3]).max() <= 1e-3, (b, np.abs(traj[:, b] - refs[b][:, 0:3]).max())
         assert np.abs(fleet.plan[b].cpu().numpy() - plans[b]).max() <= 1e-3
+
+
+def test_payload_sweep_with_true_plant_mass(pkg):
+    """BASELINE config 4 (ii): payload variant (k1 = 7) on robots whose TRUE mass is 40.05 + m_p while the MPC keeps 40.05
+    (the reference never changes `mass`, it lets theta_hat adapt).  The plant is integrated from the applied
+    contact forces.  Checked: every robot keeps solving; the CoM sags monotonically with the payload; theta_hat_z grows
+    negative monotonically with the payload and equals the estimator law theta+ = theta + (d/m)(k1 (p - p_ref) + v - v_ref)
+    (MPC file :459) integrated along the recorded CoM trajectory.  (The law's gain is d/m per tick: theta_hat_z would need
+    ~1e6 ticks to reach -m_p g; the test pins the dynamics, not the limit.)"""
+    import torch
+    from oracle.walk import load_walk
+    planner, com_ref, params, initial = load_walk()
+    B, T, k1 = 32, 120, 7.0
+    mp = np.linspace(0.0, 10.0, B)
+    fleet = pkg.Fleet(B, planner, params, com_ref, initial, k1=k1, plant_mass=params["mass"] + mp)
+    th = np.zeros(B)
+    for t in range(T):
+        pz, vz = fleet.com_pos[:, 2].cpu().numpy(), fleet.com_vel[:, 2].cpu().numpy()
+        fleet.step(t)
+        th += 0.01 / params["mass"] * (k1 * (pz - com_ref["pos_z"][t + 1]) + vz - com_ref["vel_z"][t + 1])      # reference column 0 of tick t = table row t + 1
+    assert bool(fleet.alive.all())
+    z = fleet.com_pos[:, 2].cpu().numpy(); thz = fleet.theta[:, 2].cpu().numpy()
+    assert np.all(np.diff(z) < 0) and 0.02 < z[0] - z[-1] < 0.08            # heavier payload, lower CoM (a few centimetres at 10 kg)
+    assert np.all(np.diff(thz) < 0) and thz[-1] < -1e-3
+    assert np.abs(thz - th).max() <= 1e-9 + 1e-6 * np.abs(th).max()
