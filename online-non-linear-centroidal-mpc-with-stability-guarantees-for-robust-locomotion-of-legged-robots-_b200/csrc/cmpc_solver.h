@@ -1932,11 +1932,11 @@ struct Solver {
       // saddle of the non-convex NLP -- primal feasible, complementary, dual residual stuck, regularisation at every
       // iteration -- never leaves it) is abandoned (it would run to max_iter: jammed at a saddle of the non-convex NLP, or diverging); the caller
       // retries from another start
-      if (c.stall_window > 0) {
+      if (c.stall_window > 0 || c.stall_final > 0) {
         double p2[3];
         const double emu = kkt_error(ev, mu, nrows, p2);
         if (stall_ref < 0.0) { stall_ref = emu; stall_it = it; }
-        else if (it - stall_it >= (mu <= c.mu_final ? c.stall_final : c.stall_window)) {
+        else if ((mu <= c.mu_final ? c.stall_final : c.stall_window) > 0 && it - stall_it >= (mu <= c.mu_final ? c.stall_final : c.stall_window)) {
           if (emu > 0.5 * stall_ref) { status = ST_STALL; break; }
           stall_ref = emu; stall_it = it;
         }
