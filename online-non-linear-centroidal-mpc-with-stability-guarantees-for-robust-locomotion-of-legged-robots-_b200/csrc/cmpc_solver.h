@@ -502,15 +502,12 @@ struct Solver {
       }
     }
     if (warm == 4) {
-      // automatic: shift when a contact switch lies inside the horizon (it moves one stage per tick, so the previous tick's
-      // stage i + 1 is the better start for stage i), else keep the stage alignment (references move 1.5 mm per tick)
+      // automatic: shift while a landing lies inside the horizon (the switch moves one stage per tick, so the previous tick's
+      // stage i + 1 is the better start for stage i: 20-27 instead of 26-36 iterations on those ticks), else keep the stage
+      // alignment (references move 1.5 mm per tick: 5-6 instead of 8 iterations)
       bool sw = false;
-      const int kind = (int)c.xp[1];
-      for (int i = 1; i <= N; ++i) {
-        const double a0 = i_gamma()[2 * i - 2], a1 = i_gamma()[2 * i - 1], b0 = i_gamma()[2 * i], b1 = i_gamma()[2 * i + 1];
-        if (kind == 0) sw = sw || (b0 > a0) || (b1 > a1);            // landing
-        else sw = sw || (b0 != a0) || (b1 != a1);                    // any switch
-      }
+      for (int i = 1; i <= N; ++i)                                   // a landing: a foot's gamma going 0 -> 1
+        sw = sw || (i_gamma()[2 * i] > i_gamma()[2 * i - 2]) || (i_gamma()[2 * i + 1] > i_gamma()[2 * i - 1]);
       warm = sw ? 3 : 2;
     }
     if (warm == 3) {
@@ -1794,7 +1791,6 @@ struct Solver {
       const double s0 = gS()[t], l0 = gLAM()[t], dsr = gDS()[t];
       const double dl = -l0 + mu / s0 - l0 / s0 * dsr;
       double sn = s0 + alpha * dsr, ln = l0 + a_d * dl;
-      if (c.xp[0] > 0.0) { ln = l0 + dl; const double fl = (1.0 - c.xp[0]) * l0; ln = ln < fl ? fl : ln; }
       const double lo = mu / (1e10 * sn), hi = 1e10 * mu / sn;       // IPOPT eq. (16)
       ln = ln < lo ? lo : (ln > hi ? hi : ln);
       gS()[t] = sn; gLAM()[t] = ln;

@@ -40,7 +40,7 @@ void hostsim_trace(int on) { cmpc::cmpc_trace_on = on; }
 
 int hostsim_work_doubles(int N) { return (int)work_doubles(N); }
 
-// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min, warm_push, warm_comp, xp0..xp7} (NaN = keep default)
+// cfg_over: {eps_reg, relax, mu_init, mu_final, tol, max_iter, ls_max, w_rate, mu_warm, kappa_eps, kappa_mu, theta_mu, tau_min, warm_push, warm_comp, (8 unused), stall_window, stall_final} (NaN = keep default)
 // Debug: stage-i Lagrangian gradient (60) and assembled stage block M (60x60, lower) at the iterate stored in
 // `work` (X, U, Y, S, LAM as laid out by carve_work).  Used by tests to check the analytic Hessian by finite
 // differences of the analytic gradient.
@@ -150,7 +150,6 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[14] == cfg_over[14]) c.warm_comp = cfg_over[14];
     if (cfg_over[23] == cfg_over[23]) c.stall_window = (int)cfg_over[23];
     if (cfg_over[24] == cfg_over[24]) c.stall_final = (int)cfg_over[24];
-    for (int j = 0; j < 8; ++j) if (cfg_over[15 + j] == cfg_over[15 + j]) c.xp[j] = cfg_over[15 + j];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);
