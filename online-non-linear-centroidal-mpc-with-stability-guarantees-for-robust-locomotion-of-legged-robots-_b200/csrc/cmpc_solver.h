@@ -1390,38 +1390,44 @@ struct Solver {
       }
       CMPC_TOC(sm, PF_CHOL);
       // ---- gains: K = -L^-T L_S', k = -L^-T l_m (one right-hand side per thread, registers, L broadcast from
-      // shared memory); results overwrite L_S / l_m in place.  Then stream K, k, P, p out for the forward sweep.
-      for (int t = tid; t < NX + 1; t += nt) {
-        double* rowp = sm.M + mi(t < NX ? XO + t : GR, 0);
-        double v[NA];
+      // shared memory), staged in W.  The 29 right-hand sides occupy warp 0 only; the other warps copy the cost-to-go
+      // P, p (final since the factorisation) out of the stage block meanwhile -- to shared memory for the next stage and
+      // to the scratch for the costates of the forward sweep.  Then K, k are streamed out by everybody.
+      if (nw == 1 || wid == 0) {
+        for (int t = tid; t < NX + 1; t += nt) {
+          double* rowp = sm.M + mi(t < NX ? XO + t : GR, 0);
+          double v[NA];
 #pragma unroll
-        for (int q = 0; q < NA; ++q) v[q] = -rowp[q];
-
+          for (int q = 0; q < NA; ++q) v[q] = -rowp[q];
 #pragma unroll
-        for (int k = NA - 1; k >= 0; --k) {
-          const double zk = v[k] * sm.rdiag[k];
-          v[k] = zk;
-          // (chunks of eight with a scheduling fence: the row of L must not be loaded whole ahead of time, v[] needs the registers)
+          for (int k = NA - 1; k >= 0; --k) {
+            const double zk = v[k] * sm.rdiag[k];
+            v[k] = zk;
+            // (chunks of eight with a scheduling fence: the row of L must not be loaded whole ahead of time, v[] needs the registers)
 #pragma unroll
-          for (int j0 = 0; j0 < k; j0 += 8) {
+            for (int j0 = 0; j0 < k; j0 += 8) {
 #pragma unroll
-            for (int j = j0; j < j0 + 8 && j < k; ++j) v[j] -= sm.M[mi(k, j)] * zk;
-            CMPC_SCHED_FENCE();
+              for (int j = j0; j < j0 + 8 && j < k; ++j) v[j] -= sm.M[mi(k, j)] * zk;
+              CMPC_SCHED_FENCE();
+            }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < NA; ++q) sm.W[t * NA + q] = v[q];          // W (28 x 60) is free here: K staged as 29 x 34
+          for (int q = 0; q < NA; ++q) sm.W[t * NA + q] = v[q];          // W (28 x 60) is free here: K staged as 29 x 34
+        }
+      }
+      if (nw == 1 || wid > 0) {
+        const int w0 = nw == 1 ? 0 : wid - 1, ws = nw == 1 ? 1 : nw - 1;
+        for (int r = w0; r < NX; r += ws)
+          for (int cc = lane; cc < NX; cc += nl) {
+            const double v = (cc <= r) ? sm.M[mi(XO + r, XO + cc)] : sm.M[mi(XO + cc, XO + r)];
+            sm.P[r * NX + cc] = v;
+            fac[F_P + r * NX + cc] = v;
+          }
+        if (w0 == 0) for (int t = lane; t < NX; t += nl) { const double v = sm.M[mi(GR, XO + t)]; sm.pv[t] = v; fac[F_PV + t] = v; }
       }
       par.sync();
       for (int t = tid; t < (NX + 1) * NA; t += nt) fac[F_K + t] = sm.W[t];
-      for (int r = wid; r < NX; r += nw)
-        for (int cc = lane; cc < NX; cc += nl) {
-          const double v = (cc <= r) ? sm.M[mi(XO + r, XO + cc)] : sm.M[mi(XO + cc, XO + r)];
-          sm.P[r * NX + cc] = v;
-          fac[F_P + r * NX + cc] = v;
-        }
-      for (int t = tid; t < NX; t += nt) { const double v = sm.M[mi(GR, XO + t)]; sm.pv[t] = v; fac[F_PV + t] = v; }
-      par.sync();
+      // (no barrier here: the next stage begins with one before anything of W / P is written again)
       CMPC_TOC(sm, PF_STORE);
     }
     return true;
