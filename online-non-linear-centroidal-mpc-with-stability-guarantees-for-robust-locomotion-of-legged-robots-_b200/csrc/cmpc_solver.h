@@ -1318,6 +1318,11 @@ struct Solver {
           for (int kk = 0; kk < NW; ++kk) {                         // kk static: tiles stay in registers
             const int k = 4 * tk + kk;
             if (!okp) break;
+            if (kk == 1 && !((i == 0) && (sm.mask[0] & (1ull << R_HW)))) {
+              // the angular-momentum row exists at stage 0 only: elsewhere its multiplier is a decoupled dummy (diagonal -1)
+              if (tid == 0) sm.rdiag[k] = -1.0;
+              break;
+            }
             double* cb = sm.W + (nproc & 1) * 64;
             ++nproc;
 #pragma unroll
