@@ -76,6 +76,11 @@ struct ParCta {
   __device__ void wait_async() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
   static constexpr int TPT = (NTILE + CMPC_THREADS - 1) / CMPC_THREADS;      // 4x4 register tiles per thread: 120 tiles over the CTA
   static constexpr int CPT = 1;                                              // transient tiles of tile column 0 (16) per thread
+#ifndef CMPC_GAINS4
+#define CMPC_GAINS4 1
+#endif
+  static constexpr bool GAINS4 = CMPC_GAINS4 != 0 && CMPC_THREADS == 128;      // gain back substitution on four lanes per right-hand side
+  __device__ double shfl4(double v, int src) const { return __shfl_sync(0xffffffffu, v, src, 4); }
 };
 
 struct Outputs {

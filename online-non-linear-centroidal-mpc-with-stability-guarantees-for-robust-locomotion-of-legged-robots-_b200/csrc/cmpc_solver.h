@@ -1398,6 +1398,38 @@ struct Solver {
       // shared memory), staged in W.  The 29 right-hand sides occupy warp 0 only; the other warps copy the cost-to-go
       // P, p (final since the factorisation) out of the stage block meanwhile -- to shared memory for the next stage and
       // to the scratch for the costates of the forward sweep.  Then K, k are streamed out by everybody.
+      if (Par::GAINS4) {
+        // four lanes per right-hand side (8 right-hand sides per warp, all four warps): lane `sub` of a group holds the entries
+        // j = 4 jj + sub of its right-hand side; step k: the lane that owns entry k scales it and hands it to the group by a
+        // width-4 shuffle, every lane then updates its entries left of k.  A quarter of the FMAs per lane, on four warps.
+        const int sub = lane & 3, t = wid * 8 + (lane >> 2);
+        const bool live = t < NX + 1;
+        const double* rowp = sm.M + mi(live ? (t < NX ? XO + t : GR) : GR, 0);
+        double vl[(NA + 3) / 4];
+#pragma unroll
+        for (int jj = 0; jj < (NA + 3) / 4; ++jj) vl[jj] = (4 * jj + sub < NA) ? -rowp[4 * jj + sub] : 0.0;
+#pragma unroll
+        for (int k = NA - 1; k >= 0; --k) {
+          const int jk = k >> 2, own = k & 3;
+          const double zk = par.shfl4(vl[jk] * sm.rdiag[k], own);
+          if (sub == own) vl[jk] = zk;
+          const double* Lk = sm.M + mi(k, 0) + sub;
+#pragma unroll
+          for (int jj = 0; jj < jk; ++jj) vl[jj] -= Lk[4 * jj] * zk;
+          if (sub < own) vl[jk] -= Lk[4 * jk] * zk;
+        }
+        if (live) {
+#pragma unroll
+          for (int jj = 0; jj < (NA + 3) / 4; ++jj) if (4 * jj + sub < NA) sm.W[t * NA + 4 * jj + sub] = vl[jj];      // K staged as 29 x 34 in W
+        }
+        for (int r = wid; r < NX; r += nw)
+          for (int cc = lane; cc < NX; cc += nl) {
+            const double v = (cc <= r) ? sm.M[mi(XO + r, XO + cc)] : sm.M[mi(XO + cc, XO + r)];
+            sm.P[r * NX + cc] = v;
+            fac[F_P + r * NX + cc] = v;
+          }
+        for (int q = tid; q < NX; q += nt) { const double v = sm.M[mi(GR, XO + q)]; sm.pv[q] = v; fac[F_PV + q] = v; }
+      } else {
       if (nw == 1 || wid == 0) {
         for (int t = tid; t < NX + 1; t += nt) {
           double* rowp = sm.M + mi(t < NX ? XO + t : GR, 0);
@@ -1429,6 +1461,7 @@ struct Solver {
             fac[F_P + r * NX + cc] = v;
           }
         if (w0 == 0) for (int t = lane; t < NX; t += nl) { const double v = sm.M[mi(GR, XO + t)]; sm.pv[t] = v; fac[F_PV + t] = v; }
+      }
       }
       par.sync();
       for (int t = tid; t < (NX + 1) * NA; t += nt) fac[F_K + t] = sm.W[t];

@@ -31,7 +31,9 @@ struct ParSerial {
   void copy_async(double* dst, const double* src, int n) const { for (int t = 0; t < n; ++t) dst[t] = src[t]; }
   void commit_async() const {}
   void wait_async() const {}
+  double shfl4(double v, int) const { return v; }
   static constexpr int TPT = 120, CPT = 16;
+  static constexpr bool GAINS4 = false;
 };
 
 extern "C" {
