@@ -1502,10 +1502,13 @@ struct Solver {
       const double* bav = bbuf[cur];
       const double* dx = dxall + i * NX;
       for (int cidx = tid; cidx < NA; cidx += nt) {
-        double s0 = K[NX * NA + cidx], s1 = 0.0;
+        double s0 = K[NX * NA + cidx], s1 = 0.0, s2 = 0.0, s3 = 0.0;      // four accumulators: a dependent chain of 7 FMAs instead of 14
 #pragma unroll
-        for (int r = 0; r < NX; r += 2) { s0 += K[r * NA + cidx] * dx[r]; s1 += K[(r + 1) * NA + cidx] * dx[r + 1]; }
-        const double s = s0 + s1;
+        for (int r = 0; r < NX; r += 4) {
+          s0 += K[r * NA + cidx] * dx[r]; s1 += K[(r + 1) * NA + cidx] * dx[r + 1];
+          s2 += K[(r + 2) * NA + cidx] * dx[r + 2]; s3 += K[(r + 3) * NA + cidx] * dx[r + 3];
+        }
+        const double s = (s0 + s1) + (s2 + s3);
         sm.zs[cidx] = s;
         if (cidx < NU) gDU()[i * NU + cidx] = s; else gDW()[i * NW + cidx - NU] = s;
       }
@@ -1530,10 +1533,13 @@ struct Solver {
       double s;
       if (i < N) {
         const double* fac = gFAC() + (size_t)i * FACSZ;
-        double s0 = fac[F_PV + r], s1 = 0.0;
+        double s0 = fac[F_PV + r], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NX; j += 2) { s0 += fac[F_P + j * NX + r] * dx[j]; s1 += fac[F_P + (j + 1) * NX + r] * dx[j + 1]; }
-        s = s0 + s1;
+        for (int j = 0; j < NX; j += 4) {
+          s0 += fac[F_P + j * NX + r] * dx[j]; s1 += fac[F_P + (j + 1) * NX + r] * dx[j + 1];
+          s2 += fac[F_P + (j + 2) * NX + r] * dx[j + 2]; s3 += fac[F_P + (j + 3) * NX + r] * dx[j + 3];
+        }
+        s = (s0 + s1) + (s2 + s3);
       } else {
         const double* rec = gREC() + (size_t)N * RECSZ;
         s = rec[Q_GC + 32 + r] + mu * rec[Q_M1 + 32 + r] + rec[Q_M2 + 32 + r] + (rec[Q_DIAG + 32 + r] + reg) * dx[r];
