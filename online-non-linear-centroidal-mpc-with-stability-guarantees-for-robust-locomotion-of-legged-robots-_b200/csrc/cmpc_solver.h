@@ -294,6 +294,9 @@ CMPC_HD void stage_derivs(const Config& c, const Instance& in, const Work& w, in
       blk[3] = sg[2] + sg[3];                 // yy
       blk[4] = -mf * (sg[2] - sg[3]);         // yz
       blk[5] = mf * mf * (sg[0] + sg[1] + sg[2] + sg[3]) + sg[4];   // zz
+      // (the diagonal entries travel with the other diagonal terms: the assembly then writes every entry once)
+      diag[3 * v] += blk[0]; diag[3 * v + 1] += blk[3]; diag[3 * v + 2] += blk[5];
+      blk[0] = 0.0; blk[3] = 0.0; blk[5] = 0.0;
     }
     // --- Lyapunov row
     {
@@ -725,6 +728,8 @@ struct Solver {
             blk[0] = sg[0] + sg[1]; blk[2] = -mf * (sg[0] - sg[1]);
             blk[3] = sg[2] + sg[3]; blk[4] = -mf * (sg[2] - sg[3]);
             blk[5] = mf * mf * (sg[0] + sg[1] + sg[2] + sg[3]) + sg[4];
+            a_dg[0] += blk[0]; a_dg[1] += blk[3]; a_dg[2] += blk[5];        // diagonal entries travel with the other diagonal terms
+            blk[0] = 0.0; blk[3] = 0.0; blk[5] = 0.0;
           }
 #pragma unroll
           for (int q = 0; q < 6; ++q) rec[Q_FRIC + 6 * v + q] = blk[q];
@@ -979,32 +984,53 @@ struct Solver {
     }
     par.sync();
     const bool has_hw = (i == 0) && (sm.mask[0] & (1ull << R_HW));
-    for (int t = tid; t < NZ; t += nt) {
-      sm.M[mi(GR, mz(t))] = R[Q_GC + t] + mu * R[Q_M1 + t] + R[Q_M2 + t];
-      sm.M[mi(mz(t), mz(t))] = R[Q_DIAG + t] + reg;
-    }
-    if (tid == 0) {
-      sm.M[mi(NU, NU)] = -1.0 / R[Q_LSIG];
-      sm.M[mi(GR, NU)] = R[Q_LRG] + mu / R[Q_LLAM];
-      sm.M[mi(NU + 1, NU + 1)] = has_hw ? -1.0 / R[Q_HSIG] : -1.0;
-      sm.M[mi(GR, NU + 1)] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
-    }
-    par.sync();
-    // friction barrier blocks (lower triangle, within a vertex) | symmetry-term off-diagonals (-2 w_sym / 4 between
-    // same-axis components of two vertices of one foot) | rate cross terms (q_v, f_z): disjoint entries
-    for (int t = tid; t < 48 + 36 + 8; t += nt) {
-      if (t < 48) {
-        const int v = t / 6, e6 = t % 6;
-        const int rr = (e6 == 0) ? 0 : (e6 == 1 ? 1 : (e6 == 2 ? 2 : (e6 == 3 ? 1 : 2)));
-        const int cc = (e6 == 0) ? 0 : (e6 == 1 ? 0 : (e6 == 2 ? 0 : (e6 == 3 ? 1 : (e6 == 4 ? 1 : 2))));
-        sm.M[mi(3 * v + rr, 3 * v + cc)] += R[Q_FRIC + t];
-      } else if (t < 48 + 36) {
-        const int q = t - 48, e = q / 18, ax = (q % 18) / 6, pr = q % 6;
-        const int ka[6] = {1, 2, 2, 3, 3, 3}, kb[6] = {0, 0, 1, 0, 1, 2};
-        sm.M[mi(12 * e + 3 * ka[pr] + ax, 12 * e + 3 * kb[pr] + ax)] += -0.5 * c.w_sym * R[Q_GAM + e];
-      } else {
-        const int v = t - 84;
-        sm.M[mi(XO + IQ + v, 3 * v + 2)] += -2.0 * R[Q_GAMP + v / 4];
+    // ---- one phase of entries that are each written once (the block is zero): gradient row and diagonal (60 items),
+    // the two multiplier diagonals, friction off-diagonals (xz, yz within a vertex; the diagonal part is in Q_DIAG), symmetry-term
+    // off-diagonals (-2 w_sym / 4 between same-axis components of two vertices of one foot), rate cross terms (q_v, f_z),
+    // and the bilinear torque term (f_ek, p), (f_ek, p_e), (f_ek, psi_e) (rows x, cols u; cross-axis pairs only).
+    // Item ranges start at multiples of 32 where it matters: a warp stays on one code path.
+    {
+      const double y0 = R[Q_YH], y1 = R[Q_YH + 1], y2 = R[Q_YH + 2];      // delta * y_h
+      constexpr int I0 = 64, I1 = I0 + 16, I2 = I1 + 36 + 12, I3 = I2 + 8 + 24, I4 = I3 + 48, I5 = I4 + 48, I6 = I5 + 24;   // 64 | 80 | 128 | 160 | 208 | 256 | 280
+      for (int t = tid; t < I6; t += nt) {
+        if (t < I0) {
+          if (t < NZ) {
+            sm.M[mi(GR, mz(t))] = R[Q_GC + t] + mu * R[Q_M1 + t] + R[Q_M2 + t];
+            sm.M[mi(mz(t), mz(t))] = R[Q_DIAG + t] + reg;
+          } else if (t == NZ) {
+            sm.M[mi(NU, NU)] = -1.0 / R[Q_LSIG];
+            sm.M[mi(GR, NU)] = R[Q_LRG] + mu / R[Q_LLAM];
+            sm.M[mi(NU + 1, NU + 1)] = has_hw ? -1.0 / R[Q_HSIG] : -1.0;
+            sm.M[mi(GR, NU + 1)] = has_hw ? R[Q_HRG] + mu / R[Q_HLAM] : 0.0;
+          }
+        } else if (t < I1) {
+          const int q = t - I0, v = q >> 1, yz = q & 1;                     // (z, x) -> record slot 2, (z, y) -> slot 4
+          sm.M[mi(3 * v + 2, 3 * v + yz)] = R[Q_FRIC + 6 * v + (yz ? 4 : 2)];
+        } else if (t < I2) {
+          const int q = t - I1;
+          if (q < 36) {
+            const int e = q / 18, ax = (q % 18) / 6, pr = q % 6;
+            const int ka = (pr == 0) ? 1 : (pr < 3 ? 2 : 3), kb = (pr == 0 || pr == 1 || pr == 3) ? 0 : ((pr == 2 || pr == 4) ? 1 : 2);
+            sm.M[mi(12 * e + 3 * ka + ax, 12 * e + 3 * kb + ax)] = -0.5 * c.w_sym * R[Q_GAM + e];
+          }
+        } else if (t < I3) {
+          const int v = t - I2;
+          if (v < 8) sm.M[mi(XO + IQ + v, 3 * v + 2)] = -2.0 * R[Q_GAMP + v / 4];
+        } else if (t < I5) {
+          // (f, p) and (f, p_e) cross-axis pairs: 6 per vertex each
+          const int tt = (t < I4) ? t - I3 : t - I4, v = tt / 6, pq = tt % 6, e = v / 4;
+          const int a_ = pq >> 1, b_ = (a_ + 1 + (pq & 1)) % 3;              // b != a
+          // Yx = [[0, -y2, y1], [y2, 0, -y0], [-y1, y0, 0]]
+          const double yv = (a_ == 0) ? (b_ == 1 ? -y2 : y1) : (a_ == 1 ? (b_ == 0 ? y2 : -y0) : (b_ == 0 ? -y1 : y0));
+          const double val = R[Q_GAM + e] * yv;
+          if (t < I4) sm.M[mi(XO + IP + b_, 3 * v + a_)] = -val;
+          else sm.M[mi(XO + (e ? IPR : IPL) + b_, 3 * v + a_)] = val;
+        } else {
+          const int tt = t - I5, v = tt / 3, a_ = tt % 3, e = v / 4;
+          const double dx_ = R[Q_DR + 2 * v], dy_ = R[Q_DR + 2 * v + 1];
+          const double cr = (a_ == 0) ? -y2 * dy_ : (a_ == 1 ? y2 * dx_ : y0 * dy_ - y1 * dx_);   // y x (R'c), R'c = (dx_, dy_, 0)
+          sm.M[mi(XO + (e ? IPSR : IPSL), 3 * v + a_)] = R[Q_GAM + e] * cr;
+        }
       }
     }
     par.sync();
@@ -1017,28 +1043,6 @@ struct Solver {
         const int ga = g & 15, gb = g >> 4;
         const double va = ga == 0 ? gam3[0] : (ga == 1 ? gam3[1] : 1.0), vb = gb == 0 ? gam3[0] : (gb == 1 ? gam3[1] : 1.0);
         sm.M[sm.ly_m[e]] += va * vb * R[sm.ly_s[e]];
-      }
-    }
-    // bilinear torque term: (f_ek, p), (f_ek, p_e), (f_ek, psi_e) blocks (rows x, cols u); cross-axis pairs only, so
-    // no entry is shared with the Lyapunov curvature above
-    {
-      const double y0 = R[Q_YH], y1 = R[Q_YH + 1], y2 = R[Q_YH + 2];      // delta * y_h
-      const double Yx[3][3] = {{0, -y2, y1}, {y2, 0, -y0}, {-y1, y0, 0}};
-      for (int t = tid; t < 8 * 21; t += nt) {
-        const int v = t / 21, q = t % 21, e = v / 4;
-        const double ge = R[Q_GAM + e];
-        if (q < 18) {
-          const int a_ = (q % 9) / 3, b_ = q % 3;
-          if (a_ == b_) continue;
-          const double val = ge * Yx[a_][b_];
-          if (q < 9) sm.M[mi(XO + IP + b_, 3 * v + a_)] += -val;
-          else sm.M[mi(XO + (e ? IPR : IPL) + b_, 3 * v + a_)] += val;
-        } else {
-          const int a_ = q - 18;
-          const double dx_ = R[Q_DR + 2 * v], dy_ = R[Q_DR + 2 * v + 1];
-          const double cr[3] = {-y2 * dy_, y2 * dx_, y0 * dy_ - y1 * dx_};   // y x (R'c), R'c = (dx_, dy_, 0)
-          sm.M[mi(XO + (e ? IPSR : IPSL), 3 * v + a_)] += ge * cr[a_];
-        }
       }
     }
     par.sync();
