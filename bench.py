@@ -300,7 +300,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     t = lambda x: torch.as_tensor(np.ascontiguousarray(x), device=dev)
     over = {k: float(v) for k, v in (kv.split("=") for kv in a.cfg)}
-    for k in ("max_iter", "ls_max", "stall_window", "stall_final"):
+    for k in ("max_iter", "ls_max", "stall_window", "stall_final", "jam_window"):
         if k in over:
             over[k] = int(over[k])
     R = 0 if (a.no_extras or a.config != 2) else max(K, 1)           # ticks ahead for the rolling replay

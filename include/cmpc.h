@@ -61,6 +61,8 @@ typedef struct cmpc_config {
   int32_t threads;        /* threads per instance (CTA size): 128 */
   int32_t stall_window;   /* an attempt whose barrier-problem error has not halved in this many iterations is abandoned (0 = off) */
   int32_t stall_final;    /* the same at the final barrier value (a healthy end game takes 2-4 iterations) */
+  int32_t jam_window;     /* a WARM attempt is abandoned (the instance restarts cold) after this many consecutive steps shorter than 0.1 (0 = off) */
+  int32_t reserved0;
   double delta;           /* world_time_step * mpc_rate (:11) */
   double grav;            /* params['g'] (:18) */
   double mu_fric;         /* 0.5 (:41) */

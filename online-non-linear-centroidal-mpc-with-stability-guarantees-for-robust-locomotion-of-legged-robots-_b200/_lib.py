@@ -27,7 +27,8 @@ class CmpcError(RuntimeError):
 
 class _Config(ctypes.Structure):
     _fields_ = [("N", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("ls_max", ctypes.c_int32), ("threads", ctypes.c_int32),
-                ("stall_window", ctypes.c_int32), ("stall_final", ctypes.c_int32)] + \
+                ("stall_window", ctypes.c_int32), ("stall_final", ctypes.c_int32),
+                ("jam_window", ctypes.c_int32), ("reserved0", ctypes.c_int32)] + \
                [(n, ctypes.c_double) for n in ("delta", "grav", "mu_fric", "foot_half_len", "foot_half_wid", "w_h", "w_xy",
                                                "w_zc", "w_foot", "w_sym", "w_swing", "w_rate", "eps_reg", "pz_max")] + \
                [("box", ctypes.c_double * 3)] + \

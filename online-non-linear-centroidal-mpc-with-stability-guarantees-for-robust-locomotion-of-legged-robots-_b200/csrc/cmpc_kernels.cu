@@ -36,6 +36,10 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 extern __shared__ __align__(16) unsigned char cmpc_smem_raw[];     // the CTA's dynamic shared memory (one Smem)
 
+#ifndef CMPC_PREFETCH
+#define CMPC_PREFETCH 1
+#endif
+
 struct ParCta {
   template <class T> __device__ T& smem() const { return *reinterpret_cast<T*>(cmpc_smem_raw); }
   __device__ void bind(void*) const {}
@@ -72,6 +76,12 @@ struct ParCta {
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + t) : "memory");
     }
   }
+  // L2 prefetch of n doubles (one request per 128-byte line, spread over the CTA)
+  __device__ void prefetch_l2(const double* p, int n) const {
+#if CMPC_PREFETCH
+    for (int t = (int)threadIdx.x * 16; t < n; t += (int)blockDim.x * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + t));
+#endif
+  }
   __device__ void commit_async() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
   __device__ void wait_async() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
   static constexpr int TPT = (NTILE + CMPC_THREADS - 1) / CMPC_THREADS;      // 4x4 register tiles per thread: 120 tiles over the CTA
@@ -81,6 +91,7 @@ struct ParCta {
 #endif
   static constexpr bool GAINS4 = CMPC_GAINS4 != 0 && CMPC_THREADS == 128;      // gain back substitution on four lanes per right-hand side
   __device__ double shfl4(double v, int src) const { return __shfl_sync(0xffffffffu, v, src, 4); }
+  __device__ double shfl4x(double v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m, 4); }
 };
 
 struct Outputs {
@@ -377,7 +388,7 @@ int cmpc_default_config(int32_t N, cmpc_config* cfg) {
   if (!cfg || N < 1 || N > NMAX) return fail(-1, "cmpc_default_config: bad arguments (1 <= N <= 64)");
   Config c = default_config(N);
   memset(cfg, 0, sizeof(*cfg));
-  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS; cfg->stall_window = c.stall_window; cfg->stall_final = c.stall_final;
+  cfg->N = N; cfg->max_iter = c.max_iter; cfg->ls_max = c.ls_max; cfg->threads = CMPC_THREADS; cfg->stall_window = c.stall_window; cfg->stall_final = c.stall_final; cfg->jam_window = c.jam_window;
   cfg->delta = c.delta; cfg->grav = c.grav; cfg->mu_fric = c.mu_fric;
   cfg->foot_half_len = c.hl; cfg->foot_half_wid = c.hw;
   cfg->w_h = c.w_h; cfg->w_xy = c.w_xy; cfg->w_zc = c.w_zc; cfg->w_foot = c.w_foot; cfg->w_sym = c.w_sym;
@@ -391,7 +402,7 @@ int cmpc_default_config(int32_t N, cmpc_config* cfg) {
 
 static Config to_internal(const cmpc_config* u) {
   Config c = default_config(u->N);
-  c.max_iter = u->max_iter; c.ls_max = u->ls_max; c.stall_window = u->stall_window; c.stall_final = u->stall_final;
+  c.max_iter = u->max_iter; c.ls_max = u->ls_max; c.stall_window = u->stall_window; c.stall_final = u->stall_final; c.jam_window = u->jam_window;
   c.delta = u->delta; c.grav = u->grav; c.mu_fric = u->mu_fric;
   c.hl = u->foot_half_len; c.hw = u->foot_half_wid; c.w_h = u->w_h; c.w_xy = u->w_xy; c.w_zc = u->w_zc;
   c.w_foot = u->w_foot; c.w_sym = u->w_sym; c.w_swing = u->w_swing; c.w_rate = u->w_rate; c.eps_reg = u->eps_reg;

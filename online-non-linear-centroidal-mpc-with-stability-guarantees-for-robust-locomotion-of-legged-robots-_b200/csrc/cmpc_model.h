@@ -58,6 +58,7 @@ struct Config {
   int max_iter, ls_max;
   int stall_window;                 // iterations without halving the barrier-problem error before an attempt is abandoned (0 = off)
   int stall_final;                  // the same at the final barrier value
+  int jam_window;                   // consecutive steps shorter than 0.1 before a WARM attempt is abandoned (0 = off)
 };
 
 CMPC_HD Config default_config(int N) {
@@ -69,11 +70,12 @@ CMPC_HD Config default_config(int N) {
   c.pz_max = 0.76; c.box[0] = 0.01; c.box[1] = 0.005; c.box[2] = 0.00005;
   c.relax = 1e-8;
   c.mu_init = 0.1; c.mu_final = 1e-9; c.tol = 1e-8; c.kappa_eps = 10.0; c.kappa_mu = 0.2;
-  c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 1e-6; c.warm_comp = 0.0;
+  c.theta_mu = 1.5; c.tau_min = 0.99; c.bound_push = 1e-2; c.mu_warm = 1e-3; c.warm_push = 3e-5; c.warm_comp = 0.0;
   // (long horizons: off.  Measured at N = 60, 16 384 warm recorded-walk instances on one B200, converged fraction / solves
   // per second: no rule, cap 5 N iterations 99.66 % / 2954;  end-game rule with window N, cap 5 N: 99.22 % / 3513;  same, cap
   // 10 N / 3: 98.98 % / 4171;  both rules as at N = 20: 98.27 % / 3983 -- the rules abort attempts that would still converge)
   c.stall_window = N > 20 ? 0 : 60; c.stall_final = N > 20 ? 0 : 20;
+  c.jam_window = 0;
   c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
   return c;
 }

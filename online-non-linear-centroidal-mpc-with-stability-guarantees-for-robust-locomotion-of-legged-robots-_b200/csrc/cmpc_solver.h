@@ -1496,6 +1496,9 @@ struct Solver {
     static_assert(2 * FWDBUF + NZ * 4 <= NX * NZ + NX * NX, "forward staging must fit in W | P");
     static_assert((NMAX + 1) * NX <= MSZ, "dx of all stages must fit in the stage block storage");
     for (int t = tid; t < NX; t += nt) { dxall[t] = 0.0; gDX()[t] = 0.0; }
+    // the factors of the late stages were written first and have left L2 by now (the scratch of all resident CTAs exceeds it):
+    // ask for all of them at once, so the DRAM latency is paid once and not once per stage of the sequential sweep
+    par.prefetch_l2(gFAC(), N * FACSZ);
     stage_in(0, kbuf[0], bbuf[0]);
     par.wait_async();
     par.sync();
@@ -1518,14 +1521,28 @@ struct Solver {
       }
       par.sync();
       // dx_{i+1} = d + A dx + B du   (row gather over the structural pattern)
-      for (int r = tid; r < NX; r += nt) {
-        double s = K[KSZ + r];
-        for (int e = sm.csr_ptr[r]; e < sm.csr_ptr[r + 1]; ++e) {
-          const int jq = sm.csr_idx[e], j = jq >> 2;
-          s += bav[jq] * (j < NU ? sm.zs[j] : dx[j - NU]);
+      // (the angular-momentum rows have ~25 entries, a chain of dependent index -> value loads each: four lanes per row,
+      // two entries in flight per lane, summed over the group by shuffles)
+      {
+        constexpr int G = Par::GAINS4 ? 4 : 1;
+        // (every lane of a warp takes part in the shuffles: the loop bound is rounded up to whole warps, idle lanes carry an empty row)
+        const int nl_ = par.lanes(), qend = (G == 4) ? ((NX * G + nl_ - 1) / nl_) * nl_ : NX;
+        for (int q = tid; q < qend; q += nt) {
+          const int r = q / G, sub = q - r * G;
+          const bool live = r < NX;
+          const int e1 = live ? sm.csr_ptr[r + 1] : 0;
+          double s = (live && sub == 0) ? K[KSZ + r] : 0.0, s2 = 0.0;
+          int e = live ? sm.csr_ptr[r] + sub : 0;
+          for (; e + G < e1; e += 2 * G) {
+            const int jq = sm.csr_idx[e], j = jq >> 2, jq2 = sm.csr_idx[e + G], j2 = jq2 >> 2;
+            s += bav[jq] * (j < NU ? sm.zs[j] : dx[j - NU]);
+            s2 += bav[jq2] * (j2 < NU ? sm.zs[j2] : dx[j2 - NU]);
+          }
+          if (e < e1) { const int jq = sm.csr_idx[e], j = jq >> 2; s += bav[jq] * (j < NU ? sm.zs[j] : dx[j - NU]); }
+          s += s2;
+          if (G == 4) { s += par.shfl4x(s, 1); s += par.shfl4x(s, 2); }
+          if (live && sub == 0) { dxall[(i + 1) * NX + r] = s; gDX()[(i + 1) * NX + r] = s; }
         }
-        dxall[(i + 1) * NX + r] = s;
-        gDX()[(i + 1) * NX + r] = s;
       }
       par.wait_async();
       par.sync();
@@ -1950,7 +1967,7 @@ struct Solver {
     double ev[8], parts[3];
     double filt[16][2]; int nfilt = 0;
     double theta_max = 0, theta_min = 0; bool have_theta0 = false;
-    int status = ST_MAXITER, it = 0, ls_fail = 0, stall_it = 0;
+    int status = ST_MAXITER, it = 0, ls_fail = 0, stall_it = 0, jam = 0;
     double stall_ref = -1.0;
     double kkt = 0.0;
     // merit quantities of the current point (constraint violation theta, cost, sum ln s): evaluated once here, afterwards
@@ -2044,6 +2061,13 @@ struct Solver {
       }
       CMPC_TOC(sm, PF_TRIAL);
       for (int q = 0; q < 5; ++q) cur[q] = tr[q];
+      // warm-start safeguard: a warm point can sit next to the boundary of a changed active set where the fraction-to-boundary
+      // rule cuts every step (observed: 55 iterations with step lengths of 0.06 before the solve takes off, a cold start of the
+      // same tick needs 25); `jam_window` consecutive steps shorter than 0.1 abandon the warm attempt, the instance restarts cold
+      if (warm != 0 && c.jam_window > 0) {
+        jam = (alpha < 0.1) ? jam + 1 : 0;
+        if (jam >= c.jam_window) { status = ST_STALL; ++it; break; }
+      }
       { CMPC_TIC(sm); apply_step(alpha, a_d); CMPC_TOC(sm, PF_APPLY); eval(ev); CMPC_TOC(sm, PF_EVAL); }
 #ifdef CMPC_TRACE
       if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",

@@ -26,5 +26,8 @@ print(json.dumps({"cycles_per_fact": float(np.median([r[0] for r in res])), "ker
 ''' % ROOT
 for so in sys.argv[1:]:
     env = dict(os.environ, CMPC_LIB=os.path.join(ROOT, so))
-    out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
-    print(so, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:], flush=True)
+    try:                                            # a kernel that hangs must not eat the GPU budget
+        out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True, timeout=90)
+        print(so, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:], flush=True)
+    except subprocess.TimeoutExpired:
+        print(so, "TIMEOUT (hang?)", flush=True)

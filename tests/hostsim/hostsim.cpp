@@ -32,6 +32,8 @@ struct ParSerial {
   void commit_async() const {}
   void wait_async() const {}
   double shfl4(double v, int) const { return v; }
+  double shfl4x(double v, int) const { return v; }
+  void prefetch_l2(const double*, int) const {}
   static constexpr int TPT = 120, CPT = 16;
   static constexpr bool GAINS4 = false;
 };
@@ -152,6 +154,7 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[14] == cfg_over[14]) c.warm_comp = cfg_over[14];
     if (cfg_over[23] == cfg_over[23]) c.stall_window = (int)cfg_over[23];
     if (cfg_over[24] == cfg_over[24]) c.stall_final = (int)cfg_over[24];
+    if (cfg_over[25] == cfg_over[25]) c.jam_window = (int)cfg_over[25];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);
