@@ -107,9 +107,9 @@ struct Outputs {
 // to the instance.  An instance whose attempt does not converge is appended to the ring with its next attempt -- the
 // solver's own cold start (only after a warm attempt), then a ten times larger initial barrier value, then another
 // starting point (CoM states blended from x0 towards the reference) -- and is picked up by the next free slot: the
-// retries of the few hard instances overlap with the tail of the batch instead of running behind it.  A CTA that finds
-// no work waits (nanosleep polling) until every instance is resolved, because a running attempt may still queue a retry.
-struct Queue { int32_t next, head, tail, done; };      // cursor of the initial list; retry ring head / tail; resolved instances
+// retries of the few hard instances overlap with the tail of the batch instead of running behind it.  Nobody waits: a slot
+// that finds no work leaves; a slot that queues a retry loops once more and takes it itself unless another one was faster.
+struct Queue { int32_t next, head, tail, done; };      // cursor of the initial list; retry ring head / tail; resolved instances (statistics)
 
 __device__ __forceinline__ int32_t ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
 
@@ -132,19 +132,16 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
       const int i = ld_volatile(&q->next) < batch ? atomicAdd(&q->next, 1) : batch;
       if (i < batch) item = order ? order[i] : i;                 // attempt 0, longest-expected-first order (cmpc_order_kernel)
       else {
-        const long long t0 = clock64();
+        // the retry ring.  No waiting: a slot that finds it empty leaves -- whoever queues a retry later comes back through
+        // this loop itself and will find its own entry, so every entry is taken by somebody
         for (;;) {
           const int h = ld_volatile(&q->head), t = ld_volatile(&q->tail);
-          if (h < t) {
-            if (atomicCAS(&q->head, h, h + 1) != h) continue;     // another slot took it
-            int e;
-            while ((e = ld_volatile(ring + h)) < 0) { }           // (the producer publishes the entry right after reserving it)
-            item = e;
-            break;
-          }
-          if (ld_volatile(&q->done) >= batch) break;              // every instance resolved: no retry can appear any more
-          __nanosleep(2000);
-          if (clock64() - t0 > 40000000000ll) break;              // safety net (~20 s): never hang the device
+          if (h >= t) break;
+          if (atomicCAS(&q->head, h, h + 1) != h) continue;       // another slot took it
+          int e;
+          while ((e = ld_volatile(ring + h)) < 0) { }             // (the producer publishes the entry right after reserving it)
+          item = e;
+          break;
         }
       }
       sm.flag = item;

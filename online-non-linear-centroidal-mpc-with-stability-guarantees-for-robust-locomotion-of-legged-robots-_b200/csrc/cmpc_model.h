@@ -75,7 +75,7 @@ CMPC_HD Config default_config(int N) {
   // per second: no rule, cap 5 N iterations 99.66 % / 2954;  end-game rule with window N, cap 5 N: 99.22 % / 3513;  same, cap
   // 10 N / 3: 98.98 % / 4171;  both rules as at N = 20: 98.27 % / 3983 -- the rules abort attempts that would still converge)
   c.stall_window = N > 20 ? 0 : 60; c.stall_final = N > 20 ? 0 : 20;
-  c.jam_window = 0;
+  c.jam_window = 6;
   c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
   return c;
 }

@@ -2061,14 +2061,16 @@ struct Solver {
       }
       CMPC_TOC(sm, PF_TRIAL);
       for (int q = 0; q < 5; ++q) cur[q] = tr[q];
+      const double prim_before = ev[0];
+      { CMPC_TIC(sm); apply_step(alpha, a_d); CMPC_TOC(sm, PF_APPLY); eval(ev); CMPC_TOC(sm, PF_EVAL); }
       // warm-start safeguard: a warm point can sit next to the boundary of a changed active set where the fraction-to-boundary
-      // rule cuts every step (observed: 55 iterations with step lengths of 0.06 before the solve takes off, a cold start of the
-      // same tick needs 25); `jam_window` consecutive steps shorter than 0.1 abandon the warm attempt, the instance restarts cold
+      // rule cuts every step while the infeasibility GROWS (observed: 55 to 100 iterations with step lengths below 0.1 and the
+      // primal residual rising from 0.5 to 17 before the solve takes off; a cold start of the same tick needs 25).
+      // `jam_window` consecutive such steps abandon the warm attempt, the instance restarts cold.
       if (warm != 0 && c.jam_window > 0) {
-        jam = (alpha < 0.1) ? jam + 1 : 0;
+        jam = (alpha < 0.1 && ev[0] > prim_before) ? jam + 1 : 0;
         if (jam >= c.jam_window) { status = ST_STALL; ++it; break; }
       }
-      { CMPC_TIC(sm); apply_step(alpha, a_d); CMPC_TOC(sm, PF_APPLY); eval(ev); CMPC_TOC(sm, PF_EVAL); }
 #ifdef CMPC_TRACE
       if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",
                                it, cur[1], ev[0], ev[1], ev[2], ev[3], mu, reg, a_p, a_d, alpha, (int)accepted);

@@ -100,7 +100,8 @@ def test_reset_warm_mask_and_retry_accounting(pkg, golden):
     ok = cold["status"] == 0
     assert np.array_equal(mixed["iters"][mask & ok], cold["iters"][mask & ok])          # cold again, bit for bit the same solve
     assert np.array_equal(mixed["cost"][mask & ok], cold["cost"][mask & ok])
-    assert (mixed["iters"][~mask & ok] <= warm["iters"][~mask & ok] + 2).all()
+    assert mixed["iters"][~mask & ok].mean() < 0.75 * cold["iters"][~mask & ok].mean()      # the others kept their warm start
+    assert warm["iters"][ok].mean() < 0.6 * cold["iters"][ok].mean()
     s.reset_warm()
     again = s.solve_host(*args, 2)
     assert np.array_equal(again["iters"][ok], cold["iters"][ok])
