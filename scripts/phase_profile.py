@@ -20,6 +20,6 @@ for mode in (0, 2):
     solve_total, cta_total = pc.pop("solve_total", 0), pc.pop("cta_total", 0); tot = sum(pc.values()) or 1
     print(json.dumps({"N": N, "B": B, "mode": mode, "kernel_ms": st["kernel_ms"], "solves_per_s": B / st["kernel_ms"] * 1e3,
                       "iters": st["iters"], "nfact": st["nfact"], "phases_over_solve": round(tot / max(solve_total, 1), 3),
-                      "solve_over_cta": round(solve_total / max(cta_total, 1), 3), "cta_cycles_mean": cta_total / min(B, 444), "kernel_cycles": st["kernel_ms"] * 1.965e6, "conv": int((out["status"] == 0).sum()),
+                      "solve_over_cta": round(solve_total / max(cta_total, 1), 3), "cta_cycles_mean": cta_total / min(B, s.footprint()["slots"]), "kernel_cycles": st["kernel_ms"] * 1.965e6, "conv": int((out["status"] == 0).sum()),
                       "cycles_per_fact": {k: round(v / max(st["nfact"], 1)) for k, v in pc.items()},
                       "share": {k: round(v / tot, 3) for k, v in pc.items()}}), flush=True)
