@@ -72,12 +72,14 @@ def walk_tables():
     return pl, com_ref, params, initial
 
 
-def replay_workload(N, batch, seed, back=2, ahead=0):
-    """Instances = ticks of the recorded walk sampled with replacement; returns the inputs of ticks t-back .. t+ahead."""
+def replay_workload(N, batch, seed, back=2, ahead=0, headroom=None):
+    """Instances = ticks of the recorded walk sampled with replacement; returns the inputs of ticks t-back .. t+ahead.
+    `headroom` (>= ahead) fixes the range the ticks are drawn from, so the sample does not depend on `ahead`."""
+    headroom = ahead if headroom is None else max(headroom, ahead)
     rng = np.random.default_rng(seed)
     if N in (10, 20):
         w = load_ticks(N)
-        idx = rng.integers(back, len(w["x0"]) - ahead, batch)
+        idx = rng.integers(back, len(w["x0"]) - headroom, batch)
         take = lambda ii: tuple(np.ascontiguousarray(w[k][ii]) for k in ("x0", "com_ref", "foot_ref", "gamma"))
         return [take(idx + o) for o in range(-back, ahead + 1)], float(w["mass"]), float(w["k1"]), idx
     # other horizons: re-assemble from the walk's tables at the states the recorded N = 20 walk had (SURVEY.md 8d config 5)
@@ -88,7 +90,7 @@ def replay_workload(N, batch, seed, back=2, ahead=0):
     params = dict(params, N=N)
     tables, refs = PlanTables(planner.plan), ReferenceTables(com_ref, planner)
     w = load_ticks(20)
-    idx = rng.integers(back, 1970 - N - ahead - 1, batch)
+    idx = rng.integers(back, 1970 - N - headroom - 1, batch)
 
     def instance(t):
         x = w["x0"][t]
@@ -246,6 +248,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU baseline sample (0 = 128 per core, about 10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip cold-start / rolling-replay / latency / fleet extras (A/B runs, ncu captures)")
+    ap.add_argument("--samples", type=int, default=4, help="independent instance samples the timed steps cycle through (configs 2 and 5): a step is a makespan and moves by +-10 %% with the sampled ticks")
     ap.add_argument("--warm-mode", type=int, default=4, help="warm-start mode of the replay (4 = automatic shift, 2 = full, 3 = shifted)")
     ap.add_argument("--cfg", action="append", default=[], help="solver option override key=value (experiments only; the default run uses the library defaults)")
     a = ap.parse_args()
@@ -259,7 +262,8 @@ def main():
               "warm_start": ("mode %d (4 = per instance: shifted while a landing is inside the horizon, else full), device snapshot of tick t-1 restored every step" % WM)
                             if warm_replay else "cold (solver's own initial guess)",
               "launches_per_step": "cmpc_order_kernel (launch order from tick t-1's work; warm only) + cmpc_solve_kernel (persistent CTAs, retries of failed instances re-enter its work queue); two small memsets",
-              "cache": "%s", "parallelism": "instances sharded over %d GPU(s), no collective on the hot path" % world}
+              "cache": "%s", "parallelism": "instances sharded over %d GPU(s), no collective on the hot path" % world,
+              "makespan_note": "a step is the makespan of the batch on the resident CTA slots: it moves by about +-10 % with the sampled ticks / any change of the rounding (which instance is the straggler); DESIGN.md section 5"}
 
     # ------------------------------------------------------------------ reference arm: restated CPU path only
     if a.impl == "reference":
@@ -303,44 +307,61 @@ def main():
     for k in ("max_iter", "ls_max", "stall_window", "stall_final", "jam_window"):
         if k in over:
             over[k] = int(over[k])
-    R = 0 if (a.no_extras or a.config != 2) else max(K, 1)           # ticks ahead for the rolling replay
-    if warm_replay:
-        ticks, mass, k1, idx = replay_workload(N, B, seed=rank, back=2, ahead=R)
-        prev2, prev, cur = ticks[0], ticks[1], ticks[2]
-        mass_h, k1_h = np.full(B, mass), np.full(B, k1)
-    elif a.config == 3:
-        cur, mass, k1 = perturbed_workload(B, seed=1000 + rank)
-        mass_h, k1_h = np.full(B, mass), np.full(B, k1)
-    else:
-        cur, mass_h, k1 = payload_workload(B, seed=2000 + rank)
-        k1_h = np.full(B, k1)
-    solver = pkg.BatchSolver(N, B, device=local, **over)
+    R = 0 if (a.no_extras or a.config != 2) else min(max(K, 1), 32)  # ticks of the rolling replay
+    NS = max(1, a.samples) if warm_replay else 1                     # independent instance samples the steps cycle through
+    stream = torch.cuda.Stream(dev)            # the solver's launches and the timing events share this stream
+    samples = []
+    for j in range(NS):
+        smp = {}
+        if warm_replay:
+            # (the sampled ticks do not depend on the flags: always 32 ticks of headroom, of which the rolling replay uses R)
+            ticks, mass, k1, idx = replay_workload(N, B, seed=rank * NS + j, back=2, ahead=R if j == 0 else 0, headroom=32)
+            prev2, prev, cur = ticks[0], ticks[1], ticks[2]
+            mass_h, k1_h = np.full(B, mass), np.full(B, k1)
+            if j == 0:
+                ticks0 = ticks
+        elif a.config == 3:
+            cur, mass, k1 = perturbed_workload(B, seed=1000 + rank)
+            mass_h, k1_h = np.full(B, mass), np.full(B, k1)
+        else:
+            cur, mass_h, k1 = payload_workload(B, seed=2000 + rank)
+            k1_h = np.full(B, k1)
+        sv = pkg.BatchSolver(N, B, device=local, **over)
+        mass_t, k1_t = t(mass_h), t(k1_h)
+        cur_t = [t(x) for x in cur]
+        if warm_replay:
+            # the loop's steady state, untimed: tick t-2 from cold, tick t-1 warm-started from it.  The snapshot then holds what a
+            # running controller has on the device when tick t arrives: the iterate of t-1 and the work its (warm) solve took,
+            # which orders the launch of tick t (longest expected first)
+            sv.solve_device(*[t(x) for x in prev2], mass_t, k1_t, 0)
+            out = sv.solve_device(*[t(x) for x in prev], mass_t, k1_t, WM)
+            torch.cuda.synchronize()
+            sv.warm_save(B)
+        else:
+            out = sv.solve_device(*cur_t, mass_t, k1_t, 0)
+            torch.cuda.synchronize()
+        smp.update(solver=sv, cur=cur, cur_t=cur_t, mass_h=mass_h, k1_h=k1_h, mass_t=mass_t, k1_t=k1_t, out=out)
+        samples.append(smp)
+    solver, cur, cur_t, mass_h, k1_h, mass_t, k1_t, out = (samples[0][k] for k in ("solver", "cur", "cur_t", "mass_h", "k1_h", "mass_t", "k1_t", "out"))
+    ticks = ticks0 if warm_replay else None
     fp = solver.footprint()
     config["cache"] = ("iterates %.2f GB per GPU (33 KB per instance at N=20) + scratch of the %d resident CTA slots %.2f GB, streamed every iteration "
                        "(> 126 MB L2); no extra flush" % (B * fp["iterate_bytes_per_instance"] / 1e9, min(fp["slots"], B),
                                                           min(fp["slots"], B) * fp["scratch_bytes_per_slot"] / 1e9))
-    mass_t, k1_t = t(mass_h), t(k1_h)
-    cur_t = [t(x) for x in cur]
-    stream = torch.cuda.Stream(dev)            # the solver's launches and the timing events share this stream
-    if warm_replay:
-        # the loop's steady state, untimed: tick t-2 from cold, tick t-1 warm-started from it.  The snapshot then holds what a
-        # running controller has on the device when tick t arrives: the iterate of t-1 and the work its (warm) solve took,
-        # which orders the launch of tick t (longest expected first)
-        solver.solve_device(*[t(x) for x in prev2], mass_t, k1_t, 0)
-        out = solver.solve_device(*[t(x) for x in prev], mass_t, k1_t, WM)
-        torch.cuda.synchronize()
-        solver.warm_save(B)
-    else:
-        out = solver.solve_device(*cur_t, mass_t, k1_t, 0)
-        torch.cuda.synchronize()
+    config["samples"] = "%d independent instance samples (seeds %d..%d), the timed steps cycle through them" % (NS, rank * NS, rank * NS + NS - 1)
     torch.cuda.set_stream(stream)
+    step_no = [0]
 
-    def step_device():
+    def step_device(j=None):
+        if j is None:
+            j = step_no[0] % NS
+            step_no[0] += 1
+        m = samples[j]
         if warm_replay:
-            solver.warm_restore(B, stream.cuda_stream)
-            solver.solve_device(*cur_t, mass_t, k1_t, WM, out=out, stream=stream.cuda_stream)
+            m["solver"].warm_restore(B, stream.cuda_stream)
+            m["solver"].solve_device(*m["cur_t"], m["mass_t"], m["k1_t"], WM, out=m["out"], stream=stream.cuda_stream)
         else:
-            solver.solve_device(*cur_t, mass_t, k1_t, 0, out=out, stream=stream.cuda_stream)
+            m["solver"].solve_device(*m["cur_t"], m["mass_t"], m["k1_t"], 0, out=m["out"], stream=stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -357,6 +378,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]      # per-step marks inside the one timed region
+    step_no[0] = 0
     e0.record(stream)
     marks[0].record(stream)
     for k in range(K):
@@ -367,17 +389,20 @@ def main():
     total_ms = e0.elapsed_time(e1)
     step_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(K)]
     clocks = sampler.stop() if rank == 0 else None
-    status = out["status"].cpu().numpy()
-    conv = int((status == 0).sum())
-    st = solver.last_stats()                                            # last step's kernels (all steps are identical work)
-    launches_per_step = st["launches"]                                  # kernels (the two queue memsets are not kernels)
-    # per-kernel duration of a step, measured live with CUDA events on the launching stream
-    kms = []
-    for _ in range(min(K, 3)):
-        step_device()
+    # per sample: converged count, iteration statistics and the kernels' duration of one step (CUDA events on the launching stream)
+    per = []
+    for j in range(NS):
+        step_device(j)
         torch.cuda.synchronize()
-        kms.append(solver.last_stats()["kernel_ms"])
-    kernel_ms = float(np.mean(kms))
+        stj = samples[j]["solver"].last_stats()
+        stat = samples[j]["out"]["status"].cpu().numpy()
+        per.append({"conv": int((stat == 0).sum()), "nfact": stj["nfact"], "iters": stj["iters"], "kernel_ms": stj["kernel_ms"], "launches": stj["launches"], "status": stat})
+    uses = [sum(1 for k in range(K) if k % NS == j) for j in range(NS)]
+    conv = sum(per[j]["conv"] * uses[j] for j in range(NS)) / max(K, 1)          # converged instances per step, averaged over the timed steps
+    status = np.concatenate([p["status"] for p in per])
+    st = {"nfact": sum(p["nfact"] for p in per) / NS, "iters": sum(p["iters"] for p in per) / NS}
+    launches_per_step = per[0]["launches"]                            # kernels (the two queue memsets are not kernels)
+    kernel_ms = float(np.mean([p["kernel_ms"] for p in per]))
     extras = {}
     if not a.no_extras and a.config == 2:
         # ---------------------------------------------------------------- cold start of the same batch ("also report cold start")
@@ -453,19 +478,20 @@ def main():
     # ------------------------------------------------------------------ e2e through the host-buffer C-ABI call
     torch.cuda.set_stream(torch.cuda.default_stream(dev))
 
-    def step_host():
+    def step_host(j):
+        m = samples[j % NS]
         if warm_replay:
-            solver.warm_restore(B)
-            return solver.solve_host(*cur, mass_h, k1_h, WM)
-        return solver.solve_host(*cur, mass_h, k1_h, 0)
+            m["solver"].warm_restore(B)
+            return m["solver"].solve_host(*m["cur"], m["mass_h"], m["k1_h"], WM)
+        return m["solver"].solve_host(*m["cur"], m["mass_h"], m["k1_h"], 0)
 
-    for _ in range(min(W, 2)):
-        step_host()
+    for j in range(min(W, 2)):
+        step_host(j)
     barrier()
     t0 = time.perf_counter()
     conv_e2e = 0
-    for _ in range(K):
-        res = step_host()
+    for j in range(K):
+        res = step_host(j)
         conv_e2e += int((res["status"] == 0).sum())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -521,7 +547,8 @@ def main():
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if a.config == 5 else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (recorded surrogate walk, tests/golden/walk_ticks_N20.npz + walk_inputs.npz)", "config": config,
             "converged_fraction": conv_all / (B * world), "iters_per_solve": iters_all / (B * world),
-            "factorisations_per_solve": nfact_all / (B * world), "status_histogram": np.bincount(status, minlength=7).tolist(),
+            "factorisations_per_solve": nfact_all / (B * world), "status_histogram": (np.bincount(status, minlength=7) / NS).tolist(),
+            "step_ms": [round(x, 3) for x in step_ms],
             "p50_batch_latency_ms": float(np.percentile(step_ms, 50)), "max_batch_latency_ms": float(np.max(step_ms)), "single_instance_latency": lat,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * K * world, "roofline": roofline, "clocks": clocks}

@@ -1,13 +1,9 @@
 cd "$GRAFT_REPO_ROOT"
-for c in 3 4 5; do
-timeout 300 python bench.py --config $c --steps 2 --warmup 1 --no-cpu-baseline 2> gpurun_out/cfg$c.err | tee gpurun_out/bench_config${c}_1gpu.json | python -c "
+timeout 400 python bench.py --steps 8 --warmup 4 > gpurun_out/bench_r02e.json 2> gpurun_out/bench_r02e.err; tail -3 gpurun_out/bench_r02e.err; python - <<'PY'
+import json
+j=json.load(open('gpurun_out/bench_r02e.json'))
+print({k:j[k] for k in ('value','ms_per_step','iters_per_solve','converged_fraction','step_ms','gpu_launches')}, j['e2e']['value'], j['rolling_replay']['value'], j['fleet']['value'], j['roofline']['frac'], j['roofline']['kernel_ms'], j['cpu_baseline']['value'])
+PY
+timeout 200 python bench.py --config 3 --steps 2 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
 import sys, json
-j = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print({k: j[k] for k in ('value', 'ms_per_step', 'converged_fraction', 'iters_per_solve', 'status_histogram')}, j['e2e']['value'])
-"; done
-CMPC_LIB=$PWD/lib/variants/lib_prof_head.so timeout 120 python scripts/phase_profile.py 20 4096 | tail -1 > gpurun_out/phase_final.json; cat gpurun_out/phase_final.json
-timeout 200 python bench.py --horizon 10 --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import sys, json
-j = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('N=10', j['value'], j['e2e']['value'], j['single_instance_latency'])
-"
+j = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg3:', j['value'], j['converged_fraction'])"
