@@ -102,8 +102,8 @@ struct Outputs {
 };
 
 // One launch solves a tick of the whole batch, retries included.  Persistent CTAs (one per resident slot: SMs x CTAs per
-// SM) pull work from a queue in global memory: first the instances in launch order (atomic cursor `next`), then the retry
-// ring.  The scratch (Newton step, derivative records, stage factors) belongs to the CTA slot, only the iterate belongs
+// SM) pull work from a queue in global memory: the retry ring first, then the instances in launch order (atomic cursor
+// `next`).  The scratch (Newton step, derivative records, stage factors) belongs to the CTA slot, only the iterate belongs
 // to the instance.  An instance whose attempt does not converge is appended to the ring with its next attempt -- the
 // solver's own cold start (only after a warm attempt), then a ten times larger initial barrier value, then another
 // starting point (CoM states blended from x0 towards the reference) -- and is picked up by the next free slot: the
@@ -129,20 +129,22 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
   for (;;) {
     if (threadIdx.x == 0) {
       int item = -1;
-      const int i = ld_volatile(&q->next) < batch ? atomicAdd(&q->next, 1) : batch;
-      if (i < batch) item = order ? order[i] : i;                 // attempt 0, longest-expected-first order (cmpc_order_kernel)
-      else {
-        // the retry ring.  No waiting: a slot that finds it empty leaves -- whoever queues a retry later comes back through
-        // this loop itself and will find its own entry, so every entry is taken by somebody
-        for (;;) {
-          const int h = ld_volatile(&q->head), t = ld_volatile(&q->tail);
-          if (h >= t) break;
-          if (atomicCAS(&q->head, h, h + 1) != h) continue;       // another slot took it
-          int e;
-          while ((e = ld_volatile(ring + h)) < 0) { }             // (the producer publishes the entry right after reserving it)
-          item = e;
-          break;
-        }
+      // the retry ring first: a retry is a long job (a cold solve after a failed warm attempt) and must not wait for the
+      // initial list to drain -- it would then run alone behind the batch.  No waiting: a slot that finds the ring empty and
+      // the list drained leaves -- whoever queues a retry later comes back through this loop itself and will find its own
+      // entry, so every entry is taken by somebody
+      for (;;) {
+        const int h = ld_volatile(&q->head), t = ld_volatile(&q->tail);
+        if (h >= t) break;
+        if (atomicCAS(&q->head, h, h + 1) != h) continue;         // another slot took it
+        int e;
+        while ((e = ld_volatile(ring + h)) < 0) { }               // (the producer publishes the entry right after reserving it)
+        item = e;
+        break;
+      }
+      if (item < 0) {
+        const int i = ld_volatile(&q->next) < batch ? atomicAdd(&q->next, 1) : batch;
+        if (i < batch) item = order ? order[i] : i;               // attempt 0, longest-expected-first order (cmpc_order_kernel)
       }
       sm.flag = item;
     }

@@ -5,7 +5,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 for so in "$@"; do
   echo "== $so $AB_ARGS"
-  CMPC_LIB="$PWD/$so" timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras $AB_ARGS 2>&1 | python -c "
+  CMPC_LIB="$PWD/$so" timeout 600 python bench.py --steps ${AB_STEPS:-8} --warmup 3 --no-cpu-baseline --no-extras $AB_ARGS 2>&1 | python -c "
 import sys, json
 for line in sys.stdin:
     line = line.strip()

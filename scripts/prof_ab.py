@@ -19,9 +19,10 @@ for rep in range(3):
     s.warm_restore(B)
     o = s.solve_host(*cur, mass, k1, 4)
     st = s.last_stats(); pc = s.phase_cycles()
-    res.append((pc["solve_total"] / st["nfact"], st["kernel_ms"], st["nfact"] / B, int(o["iters"].max())))
+    slots = min(B, s.footprint()["slots"])
+    res.append((pc["solve_total"] / st["nfact"], st["kernel_ms"], st["nfact"] / B, int(o["iters"].max()), pc["solve_total"] / (slots * st["kernel_ms"] * 1.965e6)))
 pc.pop("cta_total"); tot = pc.pop("solve_total")
-print(json.dumps({"cycles_per_fact": float(np.median([r[0] for r in res])), "kernel_ms": float(np.median([r[1] for r in res])), "nfact": res[0][2], "max_iters": res[0][3],
+print(json.dumps({"cycles_per_fact": float(np.median([r[0] for r in res])), "kernel_ms": float(np.median([r[1] for r in res])), "nfact": res[0][2], "max_iters": res[0][3], "slot_busy": round(float(np.median([r[4] for r in res])), 3),
                   "phases": {k: round(v / st["nfact"]) for k, v in pc.items()}}))
 ''' % ROOT
 for so in sys.argv[1:]:
