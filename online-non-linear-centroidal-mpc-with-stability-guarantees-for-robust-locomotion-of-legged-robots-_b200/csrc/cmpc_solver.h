@@ -24,6 +24,12 @@
 #define CMPC_HD_NOINLINE
 #endif
 
+#ifndef CMPC_PIPE_W
+#define CMPC_PIPE_W 1      // rows of W = P [B A] whose loads are in flight together (per lane; measured: 1 is not slower than 4)
+#endif
+#ifndef CMPC_PIPE_M
+#define CMPC_PIPE_M 4      // rows of M += [B A]' W whose loads are in flight together (per warp)
+#endif
 #ifndef CMPC_SKIP_BLOCKS
 #define CMPC_SKIP_BLOCKS 1
 #endif
@@ -175,6 +181,12 @@ struct alignas(16) Smem {
   unsigned char barz[NZ * 4];    // ba_row with 0 for an empty slot
   unsigned short ly_m[NLY], ly_s[NLY];   // Lyapunov row scatter table: index into M, index of the coefficient in the record
   unsigned char ly_g[NLY];               // ... and the two gamma selectors (0: left, 1: right, 2: none), 4 bits each
+  // options, instance and workspace pointers of the running solve.  The solver object itself lives in LOCAL memory on the GPU
+  // (the interior-point loop is a function of its own), whose loads miss the thrashed L1 two times out of three: everything
+  // the passes read per item comes from this copy instead (fixed shared-memory latency, address known at compile time)
+  alignas(8) Config cfg;
+  Instance inst;
+  Work wk;
 };
 
 struct Stats { double cost, viol, kkt, mu; int iters, status, nfact, nreg; };
@@ -444,34 +456,38 @@ struct Solver {
   // (the shared-memory block is not a member: every member function takes it from the execution policy, which on the
   // GPU derives it from the CTA's dynamic shared-memory symbol -- the compiler then knows the address space and emits
   // LDS / STS instead of generic loads and stores)
-  const Config& c; const Instance& in; Work w; Par& par;
+  const Config& c0; const Instance& in0; Work w0; Par& par;    // as given; the passes read the shared-memory copies C(), IN(), W()
   double mu, reg_last, mu_scale;
   int nfact, nreg;
   bool start_blend;                           // cold start variant of the last retry
   int tile_i[Par::TPT], tile_j[Par::TPT];     // this thread's 4 x 4 register tiles of the stage block (row, column; -1 = none)
 
   CMPC_HD Solver(const Config& c_, const Instance& in_, const Work& w_, Smem& sm_, Par& par_)
-      : c(c_), in(in_), w(w_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0), start_blend(false) { par.bind(&sm_); }
+      : c0(c_), in0(in_), w0(w_), par(par_), mu(0), reg_last(0), mu_scale(1.0), nfact(0), nreg(0), start_blend(false) { par.bind(&sm_); }
+
+  CMPC_HD const Config& C() const { return par.template smem<Smem>().cfg; }
+  CMPC_HD const Instance& IN() const { return par.template smem<Smem>().inst; }
+  CMPC_HD const Work& W() const { return par.template smem<Smem>().wk; }
 
   // workspace sections, known to be global memory
-  CMPC_HD double* gX() const { double* p = w.X; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gU() const { double* p = w.U; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gY() const { double* p = w.Y; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gS() const { double* p = w.S; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gLAM() const { double* p = w.LAM; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gDX() const { double* p = w.DX; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gDU() const { double* p = w.DU; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gDS() const { double* p = w.DS; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gYN() const { double* p = w.YN; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gDW() const { double* p = w.DW; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gREC() const { double* p = w.REC; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD double* gFAC() const { double* p = w.FAC; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gX() const { double* p = W().X; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gU() const { double* p = W().U; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gY() const { double* p = W().Y; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gS() const { double* p = W().S; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gLAM() const { double* p = W().LAM; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDX() const { double* p = W().DX; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDU() const { double* p = W().DU; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDS() const { double* p = W().DS; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gYN() const { double* p = W().YN; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gDW() const { double* p = W().DW; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gREC() const { double* p = W().REC; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD double* gFAC() const { double* p = W().FAC; CMPC_ASSUME_GLOBAL(p); return p; }
 
   // instance data, global memory as well
-  CMPC_HD const double* i_x0() const { const double* p = in.x0; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD const double* i_com_ref() const { const double* p = in.com_ref; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD const double* i_foot_ref() const { const double* p = in.foot_ref; CMPC_ASSUME_GLOBAL(p); return p; }
-  CMPC_HD const double* i_gamma() const { const double* p = in.gamma; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_x0() const { const double* p = IN().x0; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_com_ref() const { const double* p = IN().com_ref; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_foot_ref() const { const double* p = IN().foot_ref; CMPC_ASSUME_GLOBAL(p); return p; }
+  CMPC_HD const double* i_gamma() const { const double* p = IN().gamma; CMPC_ASSUME_GLOBAL(p); return p; }
 
   CMPC_HD static int tri(int r, int cidx) { return r * (r + 1) / 2 + cidx; }
 
@@ -479,7 +495,7 @@ struct Solver {
   // IPOPT does), 2 = full (X, U, Y, S, LAM given).
   CMPC_HD void init_point(int warm) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     if (warm == 0) {
       for (int t = tid; t < (N + 1) * NX; t += nt) {
         const int i = t / NX, j = t % NX;
@@ -494,7 +510,7 @@ struct Solver {
         double v = 0.0;
         if (j < 24 && j % 3 == 2) {
           const double ge = (j < 12) ? gl : gr;
-          v = ge * in.mass * c.grav / (4.0 * (gl + gr > 0.5 ? gl + gr : 1.0));
+          v = ge * IN().mass * C().grav / (4.0 * (gl + gr > 0.5 ? gl + gr : 1.0));
         }
         gU()[t] = v;
       }
@@ -538,29 +554,29 @@ struct Solver {
     if (warm < 2) for (int t = tid; t < (N + 1) * NX; t += nt) gY()[t] = 0.0;
     par.sync();
     if (warm < 2) {
-      mu = c.mu_init * mu_scale;
+      mu = C().mu_init * mu_scale;
       for (int i = tid; i <= N; i += nt) {
         double x[NX], u[NU], xp[NX], g[NR];
         for (int j = 0; j < NX; ++j) x[j] = gX()[i * NX + j];
-        if (i < N) { for (int j = 0; j < NU; ++j) u[j] = gU()[i * NU + j]; dyn_step(c, in, i, x, u, xp); }
+        if (i < N) { for (int j = 0; j < NU; ++j) u[j] = gU()[i * NU + j]; dyn_step(C(), IN(), i, x, u, xp); }
         else { for (int j = 0; j < NU; ++j) u[j] = 0.0; for (int j = 0; j < NX; ++j) xp[j] = x[j]; }
-        stage_ineq(c, in, i, sm.mask[i], x, u, xp, g);
+        stage_ineq(C(), IN(), i, sm.mask[i], x, u, xp, g);
         for (int r = 0; r < NR; ++r) {
           double sv = 1.0, lv = 0.0;
-          if (sm.mask[i] & (1ull << r)) { sv = -(g[r] - c.relax); sv = sv > c.bound_push ? sv : c.bound_push; lv = 1.0; }
+          if (sm.mask[i] & (1ull << r)) { sv = -(g[r] - C().relax); sv = sv > C().bound_push ? sv : C().bound_push; lv = 1.0; }
           gS()[i * NR + r] = sv; gLAM()[i * NR + r] = lv;
         }
       }
     } else {
-      mu = c.mu_warm;
+      mu = C().mu_warm;
       // keep the previous slacks/multipliers but push them off the boundary: s >= sqrt(mu)*1e-2, lam = mu/s floor
       for (int t = tid; t < (N + 1) * NR; t += nt) {
         const int i = t / NR, r = t % NR;
         if (!(sm.mask[i] & (1ull << r))) { gS()[t] = 1.0; gLAM()[t] = 0.0; continue; }
         double sv = gS()[t], lv = gLAM()[t];
-        if (!(sv > c.warm_push)) sv = c.warm_push;
+        if (!(sv > C().warm_push)) sv = C().warm_push;
         if (!(lv > mu / sv * 1e-3)) lv = mu / sv * 1e-3;
-        if (c.warm_comp > 0.0 && lv > mu / sv * c.warm_comp) lv = mu / sv * c.warm_comp;
+        if (C().warm_comp > 0.0 && lv > mu / sv * C().warm_comp) lv = mu / sv * C().warm_comp;
         gS()[t] = sv; gLAM()[t] = lv;
       }
     }
@@ -579,9 +595,9 @@ struct Solver {
 
   CMPC_HD void eval(double* out) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     EvalScratch* es = reinterpret_cast<EvalScratch*>(sm.M);
-    const double d = c.delta, m = in.mass, k1 = in.k1;
+    const double d = C().delta, m = IN().mass, k1 = IN().k1;
     for (int i0 = 0; i0 <= N; i0 += ECH) {
       const int ns = (N + 1 - i0) < ECH ? (N + 1 - i0) : ECH;
       // ---- P0: yaw sines / cosines; role statistics cleared
@@ -603,7 +619,7 @@ struct Solver {
         const double* x = gX() + i * NX; const double* u = gU() + i * NU; const double* yn = gY() + (i + 1) * NX;
         const double* pe = x + (e ? IPR : IPL);
         const double cs = es[il].cs[e], sn = es[il].sn[e];
-        double cx, cy; corner(c, k, cx, cy);
+        double cx, cy; corner(C(), k, cx, cy);
         const double rx = cs * cx - sn * cy, ry = sn * cx + cs * cy;
         const double r0 = rx + pe[0] - x[0], r1 = ry + pe[1] - x[1], r2 = pe[2] - x[2];
         const double dr0 = -sn * cx - cs * cy, dr1 = cs * cx - sn * cy;
@@ -640,10 +656,10 @@ struct Solver {
         const uint64_t mask = sm.mask[i];
         const double gl = i_gamma()[2 * i], gr = i_gamma()[2 * i + 1];
         for (int j = 0; j < 3; ++j) { E.F[j] = gl * E.sum[j] + gr * E.sum[3 + j]; E.xph[j] = x[IH + j] + d * E.sum[6 + j]; }
-        const double q = lyapunov_grad(c, in, i, x, E.F, E.LG);
+        const double q = lyapunov_grad(C(), IN(), i, x, E.F, E.LG);
         double* st = E.st[10];
         {
-          const double sv = s[R_LYAP], lv = lam[R_LYAP], rg = q - c.relax + sv;
+          const double sv = s[R_LYAP], lv = lam[R_LYAP], rg = q - C().relax + sv;
           stat_row(st, rg, sv, lv);
           E.sc[0] = lv / sv; E.sc[1] = rg; E.sc[2] = lv;
           rec[Q_LSIG] = lv / sv; rec[Q_LRG] = rg; rec[Q_LLAM] = lv;
@@ -654,7 +670,7 @@ struct Solver {
         if (mask & (1ull << R_HW)) {
           const double ghw = E.xph[0] * E.xph[0] + E.xph[1] * E.xph[1] + E.xph[2] * E.xph[2]
                            - (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]);
-          const double sv = s[R_HW], lv = lam[R_HW], rg = ghw - c.relax + sv;
+          const double sv = s[R_HW], lv = lam[R_HW], rg = ghw - C().relax + sv;
           stat_row(st, rg, sv, lv);
           E.sc[3] = lv / sv; E.sc[4] = rg; E.sc[5] = lv;
           rec[Q_HRG] = rg;
@@ -663,7 +679,7 @@ struct Solver {
         for (int j = 0; j < 3; ++j) { rec[Q_HP + j] = E.xph[j]; rec[Q_YH + j] = d * yn[IH + j]; }
         for (int e = 0; e < 2; ++e) {
           rec[Q_GAM + e] = e ? gr : gl;
-          rec[Q_GAMP + e] = (i >= 1) ? i_gamma()[2 * (i - 1) + e] * c.w_rate : 0.0;
+          rec[Q_GAMP + e] = (i >= 1) ? i_gamma()[2 * (i - 1) + e] * C().w_rate : 0.0;
         }
       }
       par.sync();
@@ -695,29 +711,29 @@ struct Solver {
           const double ge = e ? gr : gl;
           const double* pe = x + (e ? IPR : IPL);
           const double cs = E.cs[e], sn = E.sn[e];
-          double cx, cy; corner(c, k, cx, cy);
+          double cx, cy; corner(C(), k, cx, cy);
           const double rx = cs * cx - sn * cy, ry = sn * cx + cs * cy;
           const double rr[3] = {rx + pe[0] - x[0], ry + pe[1] - x[1], pe[2] - x[2]};
           rec[Q_DR + 2 * v] = -sn * cx - cs * cy; rec[Q_DR + 2 * v + 1] = cs * cx - sn * cy;
           const double fv[3] = {u[3 * v], u[3 * v + 1], u[3 * v + 2]};
-          const double gp = (i >= 1) ? i_gamma()[2 * (i - 1) + e] * c.w_rate : 0.0;
+          const double gp = (i >= 1) ? i_gamma()[2 * (i - 1) + e] * C().w_rate : 0.0;
           const double dz = fv[2] - x[IQ + v];
           double a_gc[3], a_dg[3], a_m1[3] = {0, 0, 0}, a_m2[3] = {0, 0, 0}, a_gl[3] = {0, 0, 0};
           for (int j = 0; j < 3; ++j) {
             const double mean = 0.25 * E.sum[3 * e + j];
-            a_gc[j] = ge * 2.0 * c.w_sym * (fv[j] - mean) + (1.0 - ge) * 2.0 * c.w_swing * fv[j];
-            a_dg[j] = ge * 2.0 * c.w_sym * 0.75 + (1.0 - ge) * 2.0 * c.w_swing;
+            a_gc[j] = ge * 2.0 * C().w_sym * (fv[j] - mean) + (1.0 - ge) * 2.0 * C().w_swing * fv[j];
+            a_dg[j] = ge * 2.0 * C().w_sym * 0.75 + (1.0 - ge) * 2.0 * C().w_swing;
           }
           a_gc[2] += 2.0 * gp * dz; a_dg[2] += 2.0 * gp;
           double blk[6] = {0, 0, 0, 0, 0, 0};
           if (mask & (1ull << (R_UNI + v))) {
-            const double mf = c.mu_fric;
+            const double mf = C().mu_fric;
             const double gv[5] = {fv[0] - mf * fv[2], -fv[0] - mf * fv[2], fv[1] - mf * fv[2], -fv[1] - mf * fv[2], -fv[2]};
             double sg[5];
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
               const int r = (q < 4) ? R_FRIC + 4 * v + q : R_UNI + v;
-              const double sv = s[r], lv = lam[r], inv = cmpc_rcp(sv), rg = gv[q] - c.relax + sv, sig = lv * inv;
+              const double sv = s[r], lv = lam[r], inv = cmpc_rcp(sv), rg = gv[q] - C().relax + sv, sig = lv * inv;
               sg[q] = sig;
               stat_row(st, rg, sv, lv); rec[Q_RG + r] = rg;
               const int ax = (q < 2) ? 0 : (q < 4 ? 1 : 2);
@@ -770,16 +786,16 @@ struct Solver {
           // ---------------- CoM role: p, v, h, theta
           const double* refp = i_com_ref() + 9 * (i >= 1 ? i - 1 : 0);         // tracking reference column i-1
           const double* ref = i_com_ref() + 9 * (has_u ? i : 0);               // dynamics / Lyapunov reference column i
-          const double wz = (i >= 1) ? wz_of(c, i - 1) : 0.0;
+          const double wz = (i >= 1) ? wz_of(C(), i - 1) : 0.0;
 #pragma unroll
           for (int cidx = 0; cidx < 12; ++cidx) {
             const int j = 32 + cidx, ax = cidx % 3;
             double gcv = 0.0, dgv = 0.0, m1v = 0.0, m2v = 0.0, glv = 0.0;
             double c0 = 1.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, by = 0.0;
             if (cidx < 3) {
-              if (i >= 1) { const double wq = (cidx == 2) ? wz : c.w_xy; gcv = 2.0 * wq * (x[cidx] - refp[cidx]); dgv = 2.0 * wq; }
+              if (i >= 1) { const double wq = (cidx == 2) ? wz : C().w_xy; gcv = 2.0 * wq * (x[cidx] - refp[cidx]); dgv = 2.0 * wq; }
               if (cidx == 2 && (mask & (1ull << R_PZ))) {
-                const double sv = s[R_PZ], lv = lam[R_PZ], inv = cmpc_rcp(sv), rg = x[IP + 2] - c.pz_max - c.relax + sv, sig = lv * inv;
+                const double sv = s[R_PZ], lv = lam[R_PZ], inv = cmpc_rcp(sv), rg = x[IP + 2] - C().pz_max - C().relax + sv, sig = lv * inv;
                 stat_row(st, rg, sv, lv); rec[Q_RG + R_PZ] = rg;
                 m1v = inv; m2v = sig * rg; glv = lv; dgv += sig;
               }
@@ -795,7 +811,7 @@ struct Solver {
                 by = c0 * yn[IP + ax] + c1 * yn[IV + ax] + c2 * yn[ITH + ax];
               }
             } else if (cidx < 9) {
-              if (has_u) { gcv = 2.0 * c.w_h * x[cidx]; dgv = 2.0 * c.w_h; by = yn[cidx]; }
+              if (has_u) { gcv = 2.0 * C().w_h * x[cidx]; dgv = 2.0 * C().w_h; by = yn[cidx]; }
             } else {
               if (has_u) { glv = lamL * E.LG[cidx - 3]; by = yn[cidx]; }
             }
@@ -810,7 +826,7 @@ struct Solver {
             if (has_u) {
               double xp;
               if (cidx < 3) xp = x[cidx] + d * x[IV + cidx];
-              else if (cidx < 6) xp = x[cidx] + d * ((cidx == 5 ? -c.grav : 0.0) + E.F[ax] / m);
+              else if (cidx < 6) xp = x[cidx] + d * ((cidx == 5 ? -C().grav : 0.0) + E.F[ax] / m);
               else if (cidx < 9) xp = E.xph[ax];
               else xp = x[cidx] + (d / m) * (k1 * (x[ax] - ref[ax]) + x[IV + ax] - ref[3 + ax]);
               const double dj = xp - xn[cidx];
@@ -832,7 +848,7 @@ struct Solver {
               double gcv = 0.0, dgv = 0.0, m1v = 0.0, m2v = 0.0, glv = 0.0;
               double c1 = 0.0, c2 = 0.0, c3 = 0.0, by = 0.0;
               if (jj == 0) {
-                if (i >= 1) { gcv = 2.0 * c.w_foot * ge * (x[po] - fr[6 + e]); dgv = 2.0 * c.w_foot * ge; }
+                if (i >= 1) { gcv = 2.0 * C().w_foot * ge * (x[po] - fr[6 + e]); dgv = 2.0 * C().w_foot * ge; }
                 if (has_u) {
                   dgv += -d * ge * E.sum[15 + e];
                   c1 = d * ge * E.sum[9 + 3 * e]; c2 = d * ge * E.sum[10 + 3 * e]; c3 = d * ge * E.sum[11 + 3 * e];
@@ -841,13 +857,13 @@ struct Solver {
               } else {
                 if (i >= 1) {
                   const double err = x[cidx] - fr[3 * e + ax];
-                  gcv = 2.0 * c.w_foot * ge * err; dgv = 2.0 * c.w_foot * ge;
+                  gcv = 2.0 * C().w_foot * ge * err; dgv = 2.0 * C().w_foot * ge;
                   if (box) {
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                       const int r = R_BOX + 6 * e + 2 * ax + q;
-                      const double ja = q ? -1.0 : 1.0, gval = ja * err - c.box[ax];
-                      const double sv = s[r], lv = lam[r], inv = cmpc_rcp(sv), rg = gval - c.relax + sv, sig = lv * inv;
+                      const double ja = q ? -1.0 : 1.0, gval = ja * err - C().box[ax];
+                      const double sv = s[r], lv = lam[r], inv = cmpc_rcp(sv), rg = gval - C().relax + sv, sig = lv * inv;
                       stat_row(st, rg, sv, lv); rec[Q_RG + r] = rg;
                       m1v += ja * inv; m2v += ja * sig * rg; glv += ja * lv; dgv += sig;
                     }
@@ -875,8 +891,8 @@ struct Solver {
                 const double ad = fabs(dj); st[0] = ad > st[0] ? ad : st[0];
                 double* col = rec + Q_BA + 4 * ui;
                 col[0] = bu; col[1] = 0.0; col[2] = 0.0; col[3] = 0.0;
-                const double gu = 2.0 * c.eps_reg * uv;
-                rec[Q_GC + ui] = gu; rec[Q_DIAG + ui] = 2.0 * c.eps_reg; rec[Q_M1 + ui] = 0.0; rec[Q_M2 + ui] = 0.0;
+                const double gu = 2.0 * C().eps_reg * uv;
+                rec[Q_GC + ui] = gu; rec[Q_DIAG + ui] = 2.0 * C().eps_reg; rec[Q_M1 + ui] = 0.0; rec[Q_M2 + ui] = 0.0;
                 const double ru = gu + bu * yn[cidx];
                 stat_dual(st, ru);
 #ifdef CMPC_TRACE
@@ -908,7 +924,7 @@ struct Solver {
   // NaNs (a NaN never wins a comparison), lane 0 publishes
   CMPC_HD void reduce_acc(double* out) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N;
+    const int N = C().N;
     if (par.warp() == 0) {
       double prim = 0, dual = 0, smax = 0, smin = 1e300, ssum = 0;
       bool bad = false;
@@ -931,14 +947,14 @@ struct Solver {
   CMPC_HD int n_rows_total() const {
     Smem& sm = par.template smem<Smem>();
     int n = 0;
-    for (int i = 0; i <= c.N; ++i) n += cmpc_popcount(sm.mask[i]);
+    for (int i = 0; i <= C().N; ++i) n += cmpc_popcount(sm.mask[i]);
     return n;
   }
 
   // scaled optimality error of the barrier problem (IPOPT eq. 5/6)
   CMPC_HD double kkt_error(const double* ev, double mu_t, int nrows, double* parts) const {
     const double smax_ = 100.0;
-    const double nmult = (double)(nrows + (c.N + 1) * NX);
+    const double nmult = (double)(nrows + (C().N + 1) * NX);
     double sd = ev[4] / nmult; sd = (sd > smax_ ? sd : smax_) / smax_;
     const double a = fabs(ev[2] - mu_t), b = fabs(ev[3] - mu_t);
     const double compl_ = (nrows > 0) ? (a > b ? a : b) / sd : 0.0;
@@ -972,9 +988,26 @@ struct Solver {
       int rr[4]; double bv[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) { bv[q] = bav[4 * j + q]; rr[q] = sm.barz[4 * j + q]; }       // (empty slots hold 0 in the record)
-      for (int r = wid; r < NX; r += nw) {
-        const double* Pr = sm.P + r * NX;
-        sm.W[r * NZ + j] = (Pr[rr[0]] * bv[0] + Pr[rr[1]] * bv[1]) + (Pr[rr[2]] * bv[2] + Pr[rr[3]] * bv[3]);
+      // (rows in groups: every load of a group is issued before its first store -- the compiler cannot move a shared-memory
+      // load above a store that might alias it, and one row at a time is one exposed load latency per row)
+      constexpr int GW = CMPC_PIPE_W;
+      for (int r0 = wid; r0 < NX; r0 += GW * nw) {
+        double pq[GW][4];
+        // (branch-free loads from clamped rows, only the store is predicated: conditionally defined array elements would send the
+        // arrays to local memory)
+#pragma unroll
+        for (int g = 0; g < GW; ++g) {
+          const int r = r0 + g * nw;
+          const double* Pr = sm.P + (r < NX ? r : NX - 1) * NX;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pq[g][q] = Pr[rr[q]];
+        }
+#pragma unroll
+        for (int g = 0; g < GW; ++g) {
+          const int r = r0 + g * nw;
+          const double v = (pq[g][0] * bv[0] + pq[g][1] * bv[1]) + (pq[g][2] * bv[2] + pq[g][3] * bv[3]);
+          if (r < NX) sm.W[r * NZ + j] = v;
+        }
       }
     }
     for (int r = tid; r < NX; r += nt) {
@@ -1011,7 +1044,7 @@ struct Solver {
           if (q < 36) {
             const int e = q / 18, ax = (q % 18) / 6, pr = q % 6;
             const int ka = (pr == 0) ? 1 : (pr < 3 ? 2 : 3), kb = (pr == 0 || pr == 1 || pr == 3) ? 0 : ((pr == 2 || pr == 4) ? 1 : 2);
-            sm.M[mi(12 * e + 3 * ka + ax, 12 * e + 3 * kb + ax)] = -0.5 * c.w_sym * R[Q_GAM + e];
+            sm.M[mi(12 * e + 3 * ka + ax, 12 * e + 3 * kb + ax)] = -0.5 * C().w_sym * R[Q_GAM + e];
           }
         } else if (t < I3) {
           const int v = t - I2;
@@ -1081,7 +1114,7 @@ struct Solver {
   // without divergence.
   CMPC_HD bool backward(double reg) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     const int lane = par.lane(), wid = par.warp(), nw = par.nwarps(), nl = par.lanes();
     par.wait_async();                                              // (a sweep abandoned on a bad pivot may have left a record copy in flight)
     {   // terminal stage: P_N diagonal, p_N = modified gradient (x part)
@@ -1106,18 +1139,41 @@ struct Solver {
       assemble_stage(i, reg, R);
       CMPC_TOC(sm, PF_ASM);
       // M += [B A]' W (lower triangle), gradient row += [B A]' tv : warp per row a, lanes over b <= a
-      for (int a_ = wid; a_ <= NZ; a_ += nw) {
-        if (a_ < NZ) {
-          int rr[4]; double bv[4];
-          if (sm.barow[4 * a_] < 0) continue;                    // structurally empty column (previous-f_z states)
+      // (rows in groups of CMPC_PIPE_M per warp: the loads of a group -- coefficients, W entries, the M entries to be updated --
+      // are all issued before its first store; one row at a time is a chain of four dependent shared-memory latencies per row,
+      // sixteen rows per warp)
+      {
+        constexpr int GM = CMPC_PIPE_M;
+        for (int a0 = wid; a0 < NZ; a0 += GM * nw) {
+          // (branch-free loads from clamped rows, only the store is predicated: conditionally defined array elements would send the
+          // arrays to local memory)
+          int rr[GM][4], mrow[GM]; double bv[GM][4]; bool on[GM];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { bv[q] = bav[4 * a_ + q]; rr[q] = sm.baofs[4 * a_ + q]; }
-          double* Mr = sm.M + mi(mz(a_), 0);
-          for (int b_ = lane; b_ <= a_; b_ += nl) {
-            const double s = (bv[0] * sm.W[rr[0] + b_] + bv[1] * sm.W[rr[1] + b_]) + (bv[2] * sm.W[rr[2] + b_] + bv[3] * sm.W[rr[3] + b_]);
-            Mr[mz(b_)] += s;
+          for (int g = 0; g < GM; ++g) {
+            const int a_ = a0 + g * nw, ac = a_ < NZ ? a_ : NZ - 1;
+            on[g] = a_ < NZ && sm.barow[4 * ac] >= 0;                      // (off: structurally empty column -- previous-f_z states)
+            mrow[g] = mi(mz(ac), 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { bv[g][q] = bav[4 * ac + q]; rr[g][q] = sm.baofs[4 * ac + q]; }
           }
-        } else {
+          const int amax = (a0 + (GM - 1) * nw < NZ) ? a0 + (GM - 1) * nw : NZ - 1;
+          for (int b_ = lane; b_ <= amax; b_ += nl) {
+            double wv[GM][4], mv[GM];
+            const int mb = mz(b_);
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) wv[g][q] = sm.W[rr[g][q] + b_];
+              mv[g] = sm.M[mrow[g] + mb];
+            }
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+              const double s = (bv[g][0] * wv[g][0] + bv[g][1] * wv[g][1]) + (bv[g][2] * wv[g][2] + bv[g][3] * wv[g][3]);
+              if (on[g] && b_ <= a0 + g * nw) sm.M[mrow[g] + mb] = mv[g] + s;
+            }
+          }
+        }
+        if (wid == NZ % nw) {                                      // gradient row
           for (int b_ = lane; b_ < NZ; b_ += nl) {
             double s = 0.0;
 #pragma unroll
@@ -1489,7 +1545,7 @@ struct Solver {
 
   CMPC_HD void forward(double reg) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     double* dxall = sm.M;                                        // dx of all stages, (N + 1) x NX: the stage block is idle here
     double* kbuf[2] = {sm.W, sm.W + FWDBUF};                     // W | P storage (contiguous, idle here)
     double* bbuf[2] = {sm.recb[0], sm.W + 2 * FWDBUF};
@@ -1575,7 +1631,7 @@ struct Solver {
   // CTA-wide: items are (stage, role) with the roles of the eval pass (8 vertices, CoM rows, foot rows).
   CMPC_HD void slack_steps(double tau, double* a_p, double* a_d, double* dphi) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     double (*st)[4] = reinterpret_cast<double (*)[4]>(sm.M);       // [(N + 1) * 10][4]: a_p, a_d, grad'dz, sum ds/s per item
     static_assert((NMAX + 1) * 10 * 4 <= MSZ + NX * NZ, "slack step scratch must fit in M | W");
     for (int t = tid; t < (N + 1) * 10; t += nt) {
@@ -1601,7 +1657,7 @@ struct Solver {
       if (role < 8) {
         const int v = role;
         if (has_u) {
-          const double f0 = du[3 * v], f1 = du[3 * v + 1], f2 = du[3 * v + 2], mf = c.mu_fric;
+          const double f0 = du[3 * v], f1 = du[3 * v + 1], f2 = du[3 * v + 2], mf = C().mu_fric;
           if (mask & (1ull << (R_UNI + v))) {
             row(R_FRIC + 4 * v + 0, -rec[Q_RG + R_FRIC + 4 * v + 0] - (f0 - mf * f2));
             row(R_FRIC + 4 * v + 1, -rec[Q_RG + R_FRIC + 4 * v + 1] - (-f0 - mf * f2));
@@ -1670,9 +1726,9 @@ struct Solver {
   // without the regularisation term), sum ln s, max unrelaxed violation.  CTA-wide like the eval pass.
   CMPC_HD void trial(double alpha, double* out) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     TrialScratch* ts = reinterpret_cast<TrialScratch*>(sm.M);
-    const double d = c.delta, m = in.mass, k1 = in.k1;
+    const double d = C().delta, m = IN().mass, k1 = IN().k1;
     for (int i0 = 0; i0 <= N; i0 += TCH) {
       const int ns = (N + 1 - i0) < TCH ? (N + 1 - i0) : TCH;
       for (int t = tid; t < ns * 2; t += nt) {
@@ -1689,7 +1745,7 @@ struct Solver {
         const double* U = gU() + i * NU; const double* DU = gDU() + i * NU;
         const int po = e ? IPR : IPL;
         const double cs = ts[il].cs[e], sn = ts[il].sn[e];
-        double cx, cy; corner(c, k, cx, cy);
+        double cx, cy; corner(C(), k, cx, cy);
         const double rx = cs * cx - sn * cy, ry = sn * cx + cs * cy;
         const double p0 = X[0] + alpha * DX[0], p1 = X[1] + alpha * DX[1], p2 = X[2] + alpha * DX[2];
         const double r0 = rx + X[po] + alpha * DX[po] - p0, r1 = ry + X[po + 1] + alpha * DX[po + 1] - p1, r2 = X[po + 2] + alpha * DX[po + 2] - p2;
@@ -1726,7 +1782,7 @@ struct Solver {
         double sprod = 1.0, smin_t = 1.0;                          // sum ln s of the item's rows (<= 12) as one logarithm of their product
         auto row = [&](int r, double g) {
           const double st = S[r] + alpha * DS[r];
-          theta += fabs(g - c.relax + st); sprod *= st; smin_t = st < smin_t ? st : smin_t; viol = g > viol ? g : viol;
+          theta += fabs(g - C().relax + st); sprod *= st; smin_t = st < smin_t ? st : smin_t; viol = g > viol ? g : viol;
         };
         auto defect = [&](int r, double xp) {
           const double ad = fabs(xp - (Xn[r] + alpha * DXn[r]));
@@ -1735,7 +1791,7 @@ struct Solver {
         if (role < 8) {
           if (has_u) {
             const int v = role, e = v >> 2;
-            const double ge = e ? gr : gl, mf = c.mu_fric;
+            const double ge = e ? gr : gl, mf = C().mu_fric;
             const double* p = E.part[v];
             const double f0 = p[0], f1 = p[1], f2 = p[2];
             if (mask & (1ull << (R_UNI + v))) {
@@ -1743,10 +1799,10 @@ struct Solver {
               row(R_FRIC + 4 * v + 2, f1 - mf * f2); row(R_FRIC + 4 * v + 3, -f1 - mf * f2);
               row(R_UNI + v, -f2);
             }
-            cost += (ge * c.w_sym + (1.0 - ge) * c.w_swing) * p[6];
+            cost += (ge * C().w_sym + (1.0 - ge) * C().w_swing) * p[6];
             if (i >= 1) {
               const double dz = f2 - (X[IQ + v] + alpha * DX[IQ + v]);
-              cost += c.w_rate * i_gamma()[2 * (i - 1) + e] * dz * dz;
+              cost += C().w_rate * i_gamma()[2 * (i - 1) + e] * dz * dz;
             }
             cref = cost;
             defect(IQ + v, f2);
@@ -1757,22 +1813,22 @@ struct Solver {
           for (int j = 0; j < 12; ++j) x[j] = X[j] + alpha * DX[j];
           if (i >= 1) {
             const double* ref = i_com_ref() + 9 * (i - 1);
-            cost += c.w_xy * ((x[0] - ref[0]) * (x[0] - ref[0]) + (x[1] - ref[1]) * (x[1] - ref[1])) + wz_of(c, i - 1) * (x[2] - ref[2]) * (x[2] - ref[2]);
+            cost += C().w_xy * ((x[0] - ref[0]) * (x[0] - ref[0]) + (x[1] - ref[1]) * (x[1] - ref[1])) + wz_of(C(), i - 1) * (x[2] - ref[2]) * (x[2] - ref[2]);
           }
-          if (mask & (1ull << R_PZ)) row(R_PZ, x[IP + 2] - c.pz_max);
+          if (mask & (1ull << R_PZ)) row(R_PZ, x[IP + 2] - C().pz_max);
           if (has_u) {
             const double* ref = i_com_ref() + 9 * i;
             double F[3], xph[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) { F[j] = gl * E.sum[j] + gr * E.sum[3 + j]; xph[j] = x[IH + j] + d * E.sum[6 + j]; }
-            cost += c.w_h * (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]);
+            cost += C().w_h * (x[IH] * x[IH] + x[IH + 1] * x[IH + 1] + x[IH + 2] * x[IH + 2]);
             // symmetry term: w_sym (sum |f_k|^2 - 4 |mean|^2) per stance foot; the first part is with the vertices
-            cost -= gl * c.w_sym * 0.25 * (E.sum[0] * E.sum[0] + E.sum[1] * E.sum[1] + E.sum[2] * E.sum[2]);
-            cost -= gr * c.w_sym * 0.25 * (E.sum[3] * E.sum[3] + E.sum[4] * E.sum[4] + E.sum[5] * E.sum[5]);
+            cost -= gl * C().w_sym * 0.25 * (E.sum[0] * E.sum[0] + E.sum[1] * E.sum[1] + E.sum[2] * E.sum[2]);
+            cost -= gr * C().w_sym * 0.25 * (E.sum[3] * E.sum[3] + E.sum[4] * E.sum[4] + E.sum[5] * E.sum[5]);
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               defect(IP + j, x[IP + j] + d * x[IV + j]);
-              defect(IV + j, x[IV + j] + d * ((j == 2 ? -c.grav : 0.0) + F[j] / m));
+              defect(IV + j, x[IV + j] + d * ((j == 2 ? -C().grav : 0.0) + F[j] / m));
               defect(IH + j, xph[j]);
               defect(ITH + j, x[ITH + j] + (d / m) * (k1 * (x[IP + j] - ref[j]) + x[IV + j] - ref[3 + j]));
             }
@@ -1780,7 +1836,7 @@ struct Solver {
               double q = 0.0;
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                const double grav = (j == 2) ? -c.grav : 0.0;
+                const double grav = (j == 2) ? -C().grav : 0.0;
                 const double vp = x[IV + j] + d * (grav + F[j] / m);
                 const double z1 = x[IP + j] + d * x[IV + j] - ref[j];
                 const double z2 = k1 * z1 + vp - ref[3 + j];
@@ -1802,17 +1858,17 @@ struct Solver {
             const int po = e ? IPSR : IPSL, xo = e ? IPR : IPL;
             const bool box = (i >= 1) && ((mask >> (R_BOX + 6 * e)) & 1ull);
             const double psi = X[po] + alpha * DX[po];
-            if (i >= 1) cost += c.w_foot * ge * (psi - fr[6 + e]) * (psi - fr[6 + e]);
-            if (has_u) { const double uv = U[30 + e] + alpha * DU[30 + e]; defect(po, psi + d * (1.0 - ge) * uv); creg += c.eps_reg * uv * uv; }
+            if (i >= 1) cost += C().w_foot * ge * (psi - fr[6 + e]) * (psi - fr[6 + e]);
+            if (has_u) { const double uv = U[30 + e] + alpha * DU[30 + e]; defect(po, psi + d * (1.0 - ge) * uv); creg += C().eps_reg * uv * uv; }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               const double xv = X[xo + j] + alpha * DX[xo + j];
               if (i >= 1) {
                 const double err = xv - fr[3 * e + j];
-                cost += c.w_foot * ge * err * err;
-                if (box) { row(R_BOX + 6 * e + 2 * j, err - c.box[j]); row(R_BOX + 6 * e + 2 * j + 1, -err - c.box[j]); }
+                cost += C().w_foot * ge * err * err;
+                if (box) { row(R_BOX + 6 * e + 2 * j, err - C().box[j]); row(R_BOX + 6 * e + 2 * j + 1, -err - C().box[j]); }
               }
-              if (has_u) { const double uv = U[24 + 3 * e + j] + alpha * DU[24 + 3 * e + j]; defect(xo + j, xv + d * (1.0 - ge) * uv); creg += c.eps_reg * uv * uv; }
+              if (has_u) { const double uv = U[24 + 3 * e + j] + alpha * DU[24 + 3 * e + j]; defect(xo + j, xv + d * (1.0 - ge) * uv); creg += C().eps_reg * uv * uv; }
             }
           }
           cref = cost; cost += creg;
@@ -1837,7 +1893,7 @@ struct Solver {
 
   CMPC_HD void reduce_trial(double* out) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N;
+    const int N = C().N;
     if (par.warp() == 0) {
       double theta = 0, cost = 0, lns = 0, viol = 0, cref = 0;
       for (int i = par.lane(); i <= N; i += par.lanes()) {
@@ -1853,7 +1909,7 @@ struct Solver {
 
   CMPC_HD void apply_step(double alpha, double a_d) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N, tid = par.tid(), nt = par.nt();
+    const int N = C().N, tid = par.tid(), nt = par.nt();
     for (int t = tid; t < (N + 1) * NX; t += nt) { gX()[t] += alpha * gDX()[t]; gY()[t] += alpha * (gYN()[t] - gY()[t]); }
     for (int t = tid; t < N * NU; t += nt) gU()[t] += alpha * gDU()[t];
     for (int t = tid; t < (N + 1) * NR; t += nt) {
@@ -1875,6 +1931,7 @@ struct Solver {
   // ---- per-solve tables: structural pattern of [B A], Lyapunov constants and scatter table, tile map
   CMPC_HD void setup() {
     Smem& sm = par.template smem<Smem>();
+    if (par.tid() == 0) { sm.cfg = c0; sm.inst = in0; sm.wk = w0; }       // (published by the barrier below)
     // structural pattern of [B A]: by column (ba_row) and by row (gather), built by the whole CTA
     for (int t = par.tid(); t < NZ * 4; t += par.nt()) {
       const int r0 = ba_row(t >> 2, t & 3);
@@ -1890,7 +1947,7 @@ struct Solver {
       int k = before;
       for (int t = 0; t < NZ * 4; ++t) if (sm.barow[t] == r) sm.csr_idx[k++] = (unsigned char)t;
     }
-    if (par.tid() == 0) lyapunov_consts(c, in, sm.lyapC);
+    if (par.tid() == 0) lyapunov_consts(C(), IN(), sm.lyapC);
     // Lyapunov row: which entries of the stage block it touches, with which coefficient.  Touched variable a (0..32):
     // forces 0..23 (type F, scaled by gamma_e), then p, v, theta; curvature lam * C (x) I_3 couples same-axis pairs only.
     for (int e = par.tid(); e < NLY; e += par.nt()) {
@@ -1956,9 +2013,9 @@ struct Solver {
   // ---- the interior-point loop (kept a function of its own on the device: inlined into the kernel it costs kilobytes of spills)
   CMPC_HD_NOINLINE void run_once(int warm, Stats* st) {
     Smem& sm = par.template smem<Smem>();
-    const int N = c.N;
+    const int N = C().N;
     double pviol;
-    if (par.tid() == 0) { build_masks(c, in, sm.mask, &pviol); sm.red[0] = pviol; }
+    if (par.tid() == 0) { build_masks(C(), IN(), sm.mask, &pviol); sm.red[0] = pviol; }
     par.sync();
     pviol = sm.red[0];
     par.sync();
@@ -1979,18 +2036,18 @@ struct Solver {
     par.sync();
     trial(0.0, cur);
     eval(ev);
-    for (it = 0; it <= c.max_iter; ++it) {
-      kkt = kkt_error(ev, c.mu_final, nrows, parts);
+    for (it = 0; it <= C().max_iter; ++it) {
+      kkt = kkt_error(ev, C().mu_final, nrows, parts);
       if (!(ev[0] == ev[0]) || !(ev[1] == ev[1]) || !(cur[1] == cur[1])) { status = ST_NAN; break; }
-      if (mu <= c.mu_final && kkt <= c.tol) { status = ST_CONVERGED; break; }
-      if (it == c.max_iter) break;
+      if (mu <= C().mu_final && kkt <= C().tol) { status = ST_CONVERGED; break; }
+      if (it == C().max_iter) break;
       // monotone barrier update (IPOPT eq. 7)
-      while (mu > c.mu_final) {
+      while (mu > C().mu_final) {
         double p2[3];
         const double emu = kkt_error(ev, mu, nrows, p2);
-        if (emu > c.kappa_eps * mu) break;
-        double m1 = c.kappa_mu * mu, m2 = pow(mu, c.theta_mu);
-        mu = m1 < m2 ? m1 : m2; if (mu < c.mu_final) mu = c.mu_final;
+        if (emu > C().kappa_eps * mu) break;
+        double m1 = C().kappa_mu * mu, m2 = pow(mu, C().theta_mu);
+        mu = m1 < m2 ? m1 : m2; if (mu < C().mu_final) mu = C().mu_final;
         nfilt = 0;
         stall_it = it; stall_ref = -1.0;
       }
@@ -1999,16 +2056,16 @@ struct Solver {
       // saddle of the non-convex NLP -- primal feasible, complementary, dual residual stuck, regularisation at every
       // iteration -- never leaves it) is abandoned (it would run to max_iter: jammed at a saddle of the non-convex NLP, or diverging); the caller
       // retries from another start
-      if (c.stall_window > 0 || c.stall_final > 0) {
+      if (C().stall_window > 0 || C().stall_final > 0) {
         double p2[3];
         const double emu = kkt_error(ev, mu, nrows, p2);
         if (stall_ref < 0.0) { stall_ref = emu; stall_it = it; }
-        else if ((mu <= c.mu_final ? c.stall_final : c.stall_window) > 0 && it - stall_it >= (mu <= c.mu_final ? c.stall_final : c.stall_window)) {
+        else if ((mu <= C().mu_final ? C().stall_final : C().stall_window) > 0 && it - stall_it >= (mu <= C().mu_final ? C().stall_final : C().stall_window)) {
           if (emu > 0.5 * stall_ref) { status = ST_STALL; break; }
           stall_ref = emu; stall_it = it;
         }
       }
-      const double tau = (1.0 - mu) > c.tau_min ? (1.0 - mu) : c.tau_min;
+      const double tau = (1.0 - mu) > C().tau_min ? (1.0 - mu) : C().tau_min;
       // factorise, regularising as IPOPT does when the input block is not positive definite
       double reg = 0.0; bool ok = false;
       for (int attempt = 0; attempt < 40; ++attempt) {
@@ -2032,7 +2089,7 @@ struct Solver {
       if (!have_theta0) { have_theta0 = true; theta_max = 1e4 * (theta > 1.0 ? theta : 1.0); theta_min = 1e-4 * (theta > 1.0 ? theta : 1.0); }
       double alpha = a_p; bool accepted = false; double tr[5];
       CMPC_TIC(sm);
-      for (int ls = 0; ls < c.ls_max; ++ls) {
+      for (int ls = 0; ls < C().ls_max; ++ls) {
         trial(alpha, tr);
         const double th_t = tr[0], ph_t = tr[1] - mu * tr[2];
         bool okf = (th_t == th_t) && (ph_t == ph_t) && th_t <= theta_max;
@@ -2067,9 +2124,9 @@ struct Solver {
       // rule cuts every step while the infeasibility GROWS (observed: 55 to 100 iterations with step lengths below 0.1 and the
       // primal residual rising from 0.5 to 17 before the solve takes off; a cold start of the same tick needs 25).
       // `jam_window` consecutive such steps abandon the warm attempt, the instance restarts cold.
-      if (warm != 0 && c.jam_window > 0) {
+      if (warm != 0 && C().jam_window > 0) {
         jam = (alpha < 0.1 && ev[0] > prim_before) ? jam + 1 : 0;
-        if (jam >= c.jam_window) { status = ST_STALL; ++it; break; }
+        if (jam >= C().jam_window) { status = ST_STALL; ++it; break; }
       }
 #ifdef CMPC_TRACE
       if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",

@@ -1,8 +1,7 @@
 cd "$GRAFT_REPO_ROOT"
-# per-phase cycles with 1 / 2 / 3 / 4 resident CTAs per SM (shared-memory padding): which phases inflate when CTAs share an SM?
-for pad in 120000 60000 20000 0; do
-  echo "== pad $pad"
-  CMPC_SMEM_PAD=$pad CMPC_LIB=$PWD/lib/variants/lib_prof_head.so timeout 200 python scripts/phase_profile.py 20 4096 | tail -1 | tee gpurun_out/phase_pad$pad.json | python -c "
+for c in 5 3; do
+timeout 300 python bench.py --config $c --steps 2 --warmup 1 --no-cpu-baseline 2> gpurun_out/cfg$c.err | tee gpurun_out/bench_config${c}_1gpu_retry.json | python -c "
 import sys, json
-j = json.loads(sys.stdin.read()); print(j['kernel_ms'], j['nfact'], j['cta_cycles_mean'], j['cycles_per_fact'])"
-done
+j = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print({k: j[k] for k in ('value', 'ms_per_step', 'converged_fraction', 'iters_per_solve', 'factorisations_per_solve', 'status_histogram')}, j['e2e']['value'])
+"; done
