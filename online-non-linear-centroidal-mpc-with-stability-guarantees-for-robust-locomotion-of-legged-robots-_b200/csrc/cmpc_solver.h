@@ -167,6 +167,7 @@ struct alignas(16) Smem {
   double zs[NA];
   double dpub[10];           // factored diagonal tile: reciprocal diagonal (4) and strict lower part (6)
   double rdiag[NA];          // reciprocal of the stored diagonal of L
+  unsigned char pzf[16];     // per tile row of the current pivot panel: 1 = the tile is exactly zero
   double lyapC[16];          // curvature of the Lyapunov row in (p, v, theta, F) space (per instance)
   double red[2];
   double red5[5];            // block-wide reduction results (written by lane 0 of warp 0)
@@ -1266,6 +1267,13 @@ struct Solver {
           const double* d = sm.dpub;
           const double i0 = d[0], i1 = d[1], i2 = d[2], i3 = d[3], l10 = d[4], l20 = d[5], l21 = d[6], l30 = d[7], l31 = d[8], l32 = d[9];
           double* pl = (sm.W + 128) + PSTR * ti;
+          // a tile that is exactly zero (rows without coupling to this block: the stage block is sparse) stays zero, is not
+          // published, and every update that would read it is skipped (`pzf`)
+          bool zero = true;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) zero = zero && (t[q] == 0.0);
+          sm.pzf[ti] = zero ? 1 : 0;
+          if (zero) return;
 #pragma unroll
           for (int a_ = 0; a_ < 4; ++a_) {
             const double v0 = t[4 * a_] * i0;
@@ -1349,6 +1357,7 @@ struct Solver {
           for (int sl = 0; sl < Par::TPT; ++sl) {
             const int ti = ti_[sl], tj = tj_[sl];
             if (tj <= tk) continue;                                  // (no tile: tj = 0) tiles left of / in the block: final
+            if (sm.pzf[ti] | sm.pzf[tj]) continue;                   // a zero panel tile on either side: nothing to subtract
             const Pair* pr = reinterpret_cast<const Pair*>((sm.W + 128) + PSTR * ti);
             const Pair* pc = reinterpret_cast<const Pair*>((sm.W + 128) + PSTR * tj);
             // four rank-1 steps, one column of the panel each: eight operand registers live next to the tile
