@@ -30,6 +30,9 @@
 #ifndef CMPC_PIPE_M
 #define CMPC_PIPE_M 4      // rows of M += [B A]' W whose loads are in flight together (per warp)
 #endif
+#ifndef CMPC_RSQ64H
+#define CMPC_RSQ64H 1
+#endif
 #ifndef CMPC_SKIP_BLOCKS
 #define CMPC_SKIP_BLOCKS 1
 #endif
@@ -105,11 +108,18 @@ CMPC_HD double cmpc_rcp(double x) {
 #endif
 }
 
-// Branch-free reciprocal square root for pivots (1e-14 < x < 1e30): single-precision seed, two Newton steps in double.
+// Branch-free reciprocal square root for pivots (1e-14 < x < 1e30): hardware seed (MUFU.RSQ64H, one instruction on the high
+// word, relative error about 2^-22; the single-precision route costs two conversions, a range fix-up and the MUFU in sequence:
+// six dependent instructions on the diagonal-tile chain everybody waits for), two Newton steps in double.
 // Unlike rsqrt(double) it has no range check / slow-path branch, so two of them interleave in one instruction stream.
 CMPC_HD double cmpc_rsqrt_nb(double x) {
 #if defined(__CUDA_ARCH__)
+#if CMPC_RSQ64H
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
   double y = (double)rsqrtf((float)x);
+#endif
   const double h = 0.5 * x;
   y = y * fma(-h, y * y, 1.5);
   y = y * fma(-h, y * y, 1.5);
@@ -1293,7 +1303,7 @@ struct Solver {
         auto skip_diag = [&](double (&t)[16], int tk) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const double dq = t[5 * q], iq = cmpc_rsqrt(dq);
+            const double dq = t[5 * q], iq = cmpc_rsqrt_nb(dq);
             sm.rdiag[4 * tk + q] = iq; t[5 * q] = dq * iq;
           }
         };
@@ -1408,7 +1418,7 @@ struct Solver {
 #endif
             // an explicit multiplier has pivot -1/sigma - g'M^-1 g < 0, as small as 1/sigma
             if (!(sgn * piv > 0.0)) { okp = false; break; }    // uniform: same value for every thread
-            const double inv = cmpc_rsqrt(sgn * piv);
+            const double inv = cmpc_rsqrt_nb(sgn * piv);
             if (tid == 0) sm.rdiag[k] = sgn * inv;                 // reciprocal of the stored (signed) diagonal
 #pragma unroll
             for (int sl = 0; sl < Par::TPT; ++sl) {
@@ -2033,7 +2043,7 @@ struct Solver {
     double ev[8], parts[3];
     double filt[16][2]; int nfilt = 0;
     double theta_max = 0, theta_min = 0; bool have_theta0 = false;
-    int status = ST_MAXITER, it = 0, ls_fail = 0, stall_it = 0, jam = 0;
+    int status = ST_MAXITER, it = 0, ls_fail = 0, stall_it = 0, jam = 0, crawl = 0;
     double stall_ref = -1.0;
     double kkt = 0.0;
     // merit quantities of the current point (constraint violation theta, cost, sum ln s): evaluated once here, afterwards
@@ -2136,6 +2146,17 @@ struct Solver {
       if (warm != 0 && C().jam_window > 0) {
         jam = (alpha < 0.1 && ev[0] > prim_before) ? jam + 1 : 0;
         if (jam >= C().jam_window) { status = ST_STALL; ++it; break; }
+      }
+      // second form of the same jam (tick 867 of the recorded walk, inside the push window: 50 iterations with step lengths of
+      // 1e-2 .. 1e-6 while the infeasibility creeps DOWN from 0.9 to 0.5, then 24 healthy ones -- 68 to 96 iterations on the GPU
+      // depending on the rounding, the longest solve of every benchmark batch; cold: 36): `crawl_window` consecutive steps shorter
+      // than `crawl_alpha` abandon the warm attempt whatever the residual does.  All 1916 recorded ticks, warm (CPU build of this
+      // core): longest solve 74 -> 54 iterations, mean 11.516 -> 11.511 with a window of 12 (8: 52 / 11.55), same KKT points (cost within 5e-12).  Rejected on the same
+      // replay: a shorter stall window for warm attempts (mean 11.9 .. 13.8, other KKT points), refusing warm points with a large
+      // primal residual (mean 15.4)
+      if (warm != 0 && C().crawl_window > 0) {
+        crawl = (alpha < C().crawl_alpha) ? crawl + 1 : 0;
+        if (crawl >= C().crawl_window) { status = ST_STALL; ++it; break; }
       }
 #ifdef CMPC_TRACE
       if (cmpc_trace_on) printf("it %3d cost %.8e prim %.2e dual %.2e smax %.2e smin %.2e mu %.1e reg %.1e a_p %.2e a_d %.2e alpha %.2e acc %d\n",

@@ -155,6 +155,8 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[23] == cfg_over[23]) c.stall_window = (int)cfg_over[23];
     if (cfg_over[24] == cfg_over[24]) c.stall_final = (int)cfg_over[24];
     if (cfg_over[25] == cfg_over[25]) c.jam_window = (int)cfg_over[25];
+    if (cfg_over[26] == cfg_over[26]) c.crawl_window = (int)cfg_over[26];
+    if (cfg_over[27] == cfg_over[27]) c.crawl_alpha = cfg_over[27];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);
