@@ -18,6 +18,15 @@ using namespace cmpc;
 #ifndef CMPC_THREADS
 #define CMPC_THREADS 128     // threads per instance (CTA size)
 #endif
+#ifndef CMPC_CP16
+#define CMPC_CP16 1
+#endif
+#ifndef CMPC_BULK
+#define CMPC_BULK 0     // 1: stage records / gains by cp.async.bulk + mbarrier (one issuing thread, 1-D TMA) instead of per-thread cp.async.
+                        // Built, parity-green (all GPU tests), measured on one box: 56.5 / 56.6 ms per bench step against 55.6 / 55.6 for the
+                        // 16-byte cp.async.cg path -- the blocks are 2-8 KB, prefetched one stage ahead, and the issuing thread adds a proxy
+                        // fence and three serial issues to a stage that is latency bound; the default stays cp.async
+#endif
 #ifndef CMPC_MIN_CTAS
 #define CMPC_MIN_CTAS 4      // resident CTAs per SM the register allocation is sized for (128 registers, 20 bytes of spills; measured +3 % over 3 CTAs at 168 registers; shared memory allows no fifth)
 #endif
@@ -69,12 +78,33 @@ struct ParCta {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
-  // asynchronous global -> shared copy of n doubles, spread over the CTA (cp.async, 8 bytes per element)
+  // asynchronous global -> shared copy of n doubles, spread over the CTA: 16-byte cp.async.cg (L2 only: the scratch streams
+  // stay out of the L1 the local-memory traffic lives in).  Every block copied here has an even length and starts at an even
+  // offset of a 16-byte aligned base (records, gains; static_asserts next to the offsets)
   __device__ void copy_async(double* dst, const double* src, int n) const {
+#if CMPC_BULK
+    // one thread hands the whole block to the copy engine (cp.async.bulk, 1-D TMA): no per-thread copy instructions; completion
+    // is counted in bytes on the CTA's transaction barrier
+    if (threadIdx.x == 0) {
+      Smem& sm = smem<Smem>();
+      const unsigned mb = (unsigned)__cvta_generic_to_shared(&sm.mbar), sa = (unsigned)__cvta_generic_to_shared(dst);
+      const unsigned bytes = (unsigned)n * 8u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // earlier generic reads of the destination come first
+      asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(sa), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+#elif CMPC_CP16
+    for (int t = 2 * (int)threadIdx.x; t < n; t += 2 * (int)blockDim.x) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + t);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + t) : "memory");
+    }
+#else
     for (int t = (int)threadIdx.x; t < n; t += (int)blockDim.x) {
       const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + t);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src + t) : "memory");
     }
+#endif
   }
   // L2 prefetch of n doubles (one request per 128-byte line, spread over the CTA)
   __device__ void prefetch_l2(const double* p, int n) const {
@@ -82,8 +112,45 @@ struct ParCta {
     for (int t = (int)threadIdx.x * 16; t < n; t += (int)blockDim.x * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + t));
 #endif
   }
+#if CMPC_BULK
+  // a group = the copies issued since the last commit: thread 0 arrives on the barrier (phase g completes when the bytes of
+  // group g have landed).  Every thread counts the groups committed and the groups it has waited for (the control flow around
+  // the copies is uniform over the CTA, so the counts agree without being shared; a shared counter read before the issuing
+  // thread has bumped it would make a fast thread wait for the parity of a phase that is still to come -- a deadlock), waits for
+  // the parity of the latest group, and returns at once when nothing new has been committed
+  mutable unsigned issued = 0, waited = 0;
+  __device__ void commit_async() const {
+    if (threadIdx.x == 0) {
+      const unsigned mb = (unsigned)__cvta_generic_to_shared(&smem<Smem>().mbar);
+      asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(mb) : "memory");
+    }
+    ++issued;
+  }
+  __device__ void wait_async() const {
+    if (waited == issued) return;
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(&smem<Smem>().mbar), parity = (issued - 1u) & 1u;
+    unsigned done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+    } while (!done);
+    waited = issued;
+  }
+  // once per CTA, before the first copy
+  __device__ void async_setup() const {
+    if (threadIdx.x == 0) {
+      const unsigned mb = (unsigned)__cvta_generic_to_shared(&smem<Smem>().mbar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    issued = 0; waited = 0;
+    __syncthreads();
+  }
+#else
   __device__ void commit_async() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
   __device__ void wait_async() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  __device__ void async_setup() const {}
+#endif
   static constexpr int TPT = (NTILE + CMPC_THREADS - 1) / CMPC_THREADS;      // 4x4 register tiles per thread: 120 tiles over the CTA
   static constexpr int CPT = 1;                                              // transient tiles of tile column 0 (16) per thread
 #ifndef CMPC_GAINS4
@@ -126,6 +193,8 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
   const long long cta_t0 = clock64();
 #endif
   double* my_scratch = scratch + sstride * blockIdx.x;
+  ParCta par;                                                    // (one per CTA: it counts the copy groups of the transaction barrier)
+  par.async_setup();
   for (;;) {
     if (threadIdx.x == 0) {
       int item = -1;
@@ -163,7 +232,6 @@ cmpc_solve_kernel(Config c, int batch, const double* __restrict__ x0, const doub
     Work w = carve_work(iter + istride * b, my_scratch, N);
     int wm = 0;
     if (attempt == 0) wm = (warm != 0 && valid && !valid[b]) ? 0 : warm;        // no previous solution of this instance: cold
-    ParCta par;
     Solver<ParCta> sol(c, in, w, sm, par);
     Stats st;
 #ifdef CMPC_PROFILE

@@ -64,6 +64,8 @@ constexpr int Q_GC = 0, Q_M1 = 60, Q_M2 = 120, Q_BA = 180, Q_D = 420, Q_DIAG = 4
               Q_GAM = 593, Q_GAMP = 595, Q_DR = 600, Q_LRG = 616, Q_LLAM = 617, Q_HRG = 618,
               Q_RG = 620;                     // row residuals g - relax + s of the condensed rows (56 slots, by row)
 constexpr int RECSZ = Q_RG + NR;            // 676
+static_assert(Q_RG % 2 == 0 && Q_BA % 2 == 0 && Q_D % 2 == 0 && RECSZ % 2 == 0 && KSZ % 2 == 0 && FACSZ % 2 == 0 && NX % 2 == 0,
+              "asynchronous copies move 16-byte granules: even offsets and lengths");
 
 // optional phase timers (cycles, thread 0 of each CTA): -DCMPC_PROFILE
 #if defined(CMPC_PROFILE) && defined(__CUDA_ARCH__)
@@ -198,6 +200,8 @@ struct alignas(16) Smem {
   alignas(8) Config cfg;
   Instance inst;
   Work wk;
+  // transaction barrier of the bulk asynchronous copies (GPU execution policy)
+  alignas(8) unsigned long long mbar;
 };
 
 struct Stats { double cost, viol, kkt, mu; int iters, status, nfact, nreg; };
