@@ -3,6 +3,7 @@ execution policy (tests/hostsim -- a test aid, never a product path) against the
 Catches errors in the analytic derivatives / Riccati algebra here, where there is no GPU; the CUDA build of the
 same source is checked by tests/test_gpu_parity.py on the B200."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -109,3 +110,21 @@ def test_wide_eval_pass_matches_thread_per_stage_evaluation(golden):
             L.hostsim_eval_compare(ctypes.c_int(N), dp(x0), dp(com), dp(foot), dp(gam), ctypes.c_double(prob.mass),
                                    ctypes.c_double(prob.k1), dp(r["work"]), dp(out))
             assert out[0] <= 1e-10 and out[1] <= 1e-9 and out[8] <= 1e-10, (N, tick, out)     # summation order differs
+
+
+def test_crawling_warm_start_is_abandoned():
+    """Tick 867 of the recorded N = 20 walk (inside the push window): the warm attempt takes ~50 steps of length 1e-2 .. 1e-6 before it
+    gets going (74 iterations in all; a cold start needs 36).  The crawl rule (`crawl_window` consecutive steps shorter than
+    `crawl_alpha`) restarts it cold: the solve ends at the same KKT point in far fewer iterations; with the rule off the old count
+    comes back."""
+    w = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "walk_ticks_N20.npz")))
+    t = 867
+    r2 = hostsim.solve(problem(w, t - 2, 20))
+    r1 = hostsim.solve(problem(w, t - 1, 20), work=r2["work"].copy(), warm=4)
+    on = hostsim.solve(problem(w, t, 20), work=r1["work"].copy(), warm=4)
+    off = hostsim.solve(problem(w, t, 20), work=r1["work"].copy(), warm=4, crawl_window=0)
+    cold = hostsim.solve(problem(w, t, 20))
+    assert on["status"] == 0 and off["status"] == 0 and cold["status"] == 0
+    assert off["iters"] >= 65 and on["iters"] <= 58 and cold["iters"] <= 40, (on["iters"], off["iters"], cold["iters"])
+    assert abs(on["cost"] - off["cost"]) <= COST_TOL * max(1.0, abs(off["cost"]))
+    assert abs(on["cost"] - cold["cost"]) <= COST_TOL * max(1.0, abs(cold["cost"]))
