@@ -1,8 +1,8 @@
 """Independent pin of the oracle: scipy's trust-constr / SLSQP on the LITERAL NLP
 (oracle/spec.py, sympy derivatives), started 1e-3 away from oracle-T's answer, return to that answer within the parity
-tolerances.  tests/golden/scipy_pin.json holds the distances of 12 instances (nominal N = 10 / 20 ticks incl. standing,
-lift-off, landing, push window, last tick; payload k1 = 7 with masses 45 / 50 kg; perturbed initial states), produced by
-tests/golden/make_scipy_pin.py; two instances are repeated live here."""
+tolerances.  tests/golden/scipy_pin.json holds the distances of EVERY golden instance at N = 10 / 20 (25 + 14 nominal ticks,
+12 payload instances with k1 = 7 and three masses, 20 perturbed initial states) and of three N = 60 instances (push window,
+mid walk, last valid tick), produced by tests/golden/make_scipy_pin.py; two instances are repeated live here."""
 import json
 import os
 
@@ -16,10 +16,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_committed_scipy_cross_checks_are_within_the_parity_tolerances():
     pin = json.load(open(os.path.join(ROOT, "tests", "golden", "scipy_pin.json")))
-    assert len(pin) >= 12
+    assert len(pin) >= 74
     kinds = {(p["golden"], p["method"]) for p in pin}
     assert ("payload_N10", "trust-constr") in kinds and ("perturbed_N20", "trust-constr") in kinds and ("N10", "SLSQP") in kinds
     assert any(p["k1"] == 7.0 and p["mass"] > 44 for p in pin)
+    assert sum(1 for p in pin if p["N"] == 60) >= 3                     # the long horizon is pinned too
+    # every golden instance of the four N = 10 / 20 files is there
+    for name in ("N10", "N20", "payload_N10", "perturbed_N20"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", "golden_%s.npz" % name))
+        conv = [k for k in range(len(g["ticks"])) if "status" not in g.files or g["status"][k] == 0]
+        assert sorted(p["index"] for p in pin if p["golden"] == name) == conv, name
     for p in pin:
         assert p["start_dist"] >= 1e-3                                  # it did start away from the answer
         assert p["cost_err"] <= COST_TOL and p["x1_err"] <= X1_TOL and p["u0_err"] <= U0_TOL, p
