@@ -59,6 +59,7 @@ struct Config {
   int stall_window;                 // iterations without halving the barrier-problem error before an attempt is abandoned (0 = off)
   int stall_final;                  // the same at the final barrier value
   int jam_window;                   // consecutive steps shorter than 0.1 before a WARM attempt is abandoned (0 = off)
+  int warm_stall_window;            // stall window of a WARM attempt above the final barrier value (0 = stall_window)
   int crawl_window; double crawl_alpha;   // consecutive steps shorter than crawl_alpha, whatever the residual does (0 = off)
 };
 
@@ -77,6 +78,11 @@ CMPC_HD Config default_config(int N) {
   // 10 N / 3: 98.98 % / 4171;  both rules as at N = 20: 98.27 % / 3983 -- the rules abort attempts that would still converge)
   c.stall_window = N > 20 ? 0 : 60; c.stall_final = N > 20 ? 0 : 20;
   c.jam_window = 6;
+  // (short horizons: a warm attempt that has not halved its error in 25 iterations at one barrier value restarts cold.  All 1926
+  // recorded N = 10 ticks, warm, CPU build: longest solve 90 -> 55 iterations -- the warm attempts of ticks 473 / 772 / 1474 / 1574 sit at
+  // step lengths of 0.7 for the 60 iterations of the general window --, mean 10.69 -> 10.52, same KKT points.  At N = 20 windows of
+  // 25 / 30 lengthen the longest solve (54 -> 58 / 62) and 40 changes nothing: off)
+  c.warm_stall_window = N <= 12 ? 25 : 0;
   c.crawl_window = N > 20 ? 0 : 12; c.crawl_alpha = 0.05;    // (long horizons: off -- at N = 60 warm attempts crawl and still beat a cold start: 24.8 -> 28.1 iterations with the rule)
   c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
   return c;

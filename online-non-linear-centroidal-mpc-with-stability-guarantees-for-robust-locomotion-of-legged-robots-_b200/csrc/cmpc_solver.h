@@ -2079,11 +2079,12 @@ struct Solver {
       // saddle of the non-convex NLP -- primal feasible, complementary, dual residual stuck, regularisation at every
       // iteration -- never leaves it) is abandoned (it would run to max_iter: jammed at a saddle of the non-convex NLP, or diverging); the caller
       // retries from another start
-      if (C().stall_window > 0 || C().stall_final > 0) {
+      const int win_mid = (warm != 0 && C().warm_stall_window > 0) ? C().warm_stall_window : C().stall_window;
+      if (win_mid > 0 || C().stall_final > 0) {
         double p2[3];
         const double emu = kkt_error(ev, mu, nrows, p2);
         if (stall_ref < 0.0) { stall_ref = emu; stall_it = it; }
-        else if ((mu <= C().mu_final ? C().stall_final : C().stall_window) > 0 && it - stall_it >= (mu <= C().mu_final ? C().stall_final : C().stall_window)) {
+        else if ((mu <= C().mu_final ? C().stall_final : win_mid) > 0 && it - stall_it >= (mu <= C().mu_final ? C().stall_final : win_mid)) {
           if (emu > 0.5 * stall_ref) { status = ST_STALL; break; }
           stall_ref = emu; stall_it = it;
         }

@@ -157,6 +157,7 @@ int hostsim_solve(int N, const double* x0, const double* com_ref, const double* 
     if (cfg_over[25] == cfg_over[25]) c.jam_window = (int)cfg_over[25];
     if (cfg_over[26] == cfg_over[26]) c.crawl_window = (int)cfg_over[26];
     if (cfg_over[27] == cfg_over[27]) c.crawl_alpha = cfg_over[27];
+    if (cfg_over[28] == cfg_over[28]) c.warm_stall_window = (int)cfg_over[28];
   }
   Instance in{x0, com_ref, foot_ref, gamma, mass, k1};
   Work w = carve_work(work, N);

@@ -46,7 +46,7 @@ def solve(prob, work=None, warm=0, **over):
     L = lib()
     N = prob.N
     x0, com, foot, gam = pack(prob)
-    keys = ["eps_reg", "relax", "mu_init", "mu_final", "tol", "max_iter", "ls_max", "w_rate", "mu_warm", "kappa_eps", "kappa_mu", "theta_mu", "tau_min", "warm_push", "warm_comp"] + ["xp%d" % j for j in range(8)] + ["stall_window", "stall_final", "jam_window", "crawl_window", "crawl_alpha"]
+    keys = ["eps_reg", "relax", "mu_init", "mu_final", "tol", "max_iter", "ls_max", "w_rate", "mu_warm", "kappa_eps", "kappa_mu", "theta_mu", "tau_min", "warm_push", "warm_comp"] + ["xp%d" % j for j in range(8)] + ["stall_window", "stall_final", "jam_window", "crawl_window", "crawl_alpha", "warm_stall_window"]
     cfg = np.full(len(keys), np.nan)
     if getattr(prob, "eps_reg", None) is not None:
         over.setdefault("eps_reg", prob.eps_reg)       # None: the product default (1e-5; the oracle uses 1e-9)
