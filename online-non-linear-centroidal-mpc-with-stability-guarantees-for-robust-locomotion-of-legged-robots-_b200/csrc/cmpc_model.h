@@ -84,7 +84,10 @@ CMPC_HD Config default_config(int N) {
   // 25 / 30 lengthen the longest solve (54 -> 58 / 62) and 40 changes nothing: off)
   c.warm_stall_window = N <= 12 ? 25 : 0;
   c.crawl_window = N > 20 ? 0 : 12; c.crawl_alpha = 0.05;    // (long horizons: off -- at N = 60 warm attempts crawl and still beat a cold start: 24.8 -> 28.1 iterations with the rule)
-  c.max_iter = N > 20 ? 5 * N : 100; c.ls_max = 3;     // long horizons (several contact switches inside) need more than 100 from cold
+  // iteration cap PER ATTEMPT.  N <= 20: 70 -- an instance that fails every attempt is a serial chain of 3-4 caps on one CTA and sets the
+  // duration of a cold batch (4096 perturbed states, CPU build: same 4090 converged with 100 and 70, longest chain 300 -> 210 iterations,
+  // mean unchanged; 50 loses three instances); long horizons (several contact switches inside) need more than 100 from cold
+  c.max_iter = N > 20 ? 5 * N : 70; c.ls_max = 3;
   return c;
 }
 
