@@ -128,3 +128,18 @@ def test_crawling_warm_start_is_abandoned():
     assert off["iters"] >= 65 and on["iters"] <= 58 and cold["iters"] <= 40, (on["iters"], off["iters"], cold["iters"])
     assert abs(on["cost"] - off["cost"]) <= COST_TOL * max(1.0, abs(off["cost"]))
     assert abs(on["cost"] - cold["cost"]) <= COST_TOL * max(1.0, abs(cold["cost"]))
+
+
+def test_stalled_warm_start_at_the_short_horizon_is_abandoned_early():
+    """Tick 1574 of the recorded N = 10 walk: the warm attempt sits at step lengths of 0.7 without halving its error (60 iterations under
+    the general stall window, 90 in all; a cold start needs 30).  At N <= 12 a warm attempt gets a window of 25 (`warm_stall_window`):
+    same KKT point, 55 iterations."""
+    w = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "walk_ticks_N10.npz")))
+    t = 1574
+    r2 = hostsim.solve(problem(w, t - 2, 10))
+    r1 = hostsim.solve(problem(w, t - 1, 10), work=r2["work"].copy(), warm=4)
+    on = hostsim.solve(problem(w, t, 10), work=r1["work"].copy(), warm=4)
+    off = hostsim.solve(problem(w, t, 10), work=r1["work"].copy(), warm=4, warm_stall_window=0)
+    assert on["status"] == 0 and off["status"] == 0
+    assert off["iters"] >= 80 and on["iters"] <= 60, (on["iters"], off["iters"])
+    assert abs(on["cost"] - off["cost"]) <= COST_TOL * max(1.0, abs(off["cost"]))
