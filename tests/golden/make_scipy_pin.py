@@ -20,13 +20,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FILES = [("N10", 10), ("N20", 20), ("payload_N10", 10), ("perturbed_N20", 20)]
 N60_TICKS = (805, 1500, 1910)          # push window, mid walk, last valid tick: 1.5 - 2.5 minutes each (ticks 230 / 262 did not finish in 40)
+N60_ALTS = ((150, 2),)                 # (tick, index into X_alt / U_alt): the lower-cost KKT point scipy moves to from the primary one (6 minutes)
 
 
 def run(case):
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from oracle.scipy_check import cross_check
     from parity import COST_TOL, U0_TOL, X1_TOL, u0_err
-    name, N, k = case
+    name, N, k = case[:3]
+    alt = case[3] if len(case) > 3 else None
     g = np.load(os.path.join(HERE, "golden_%s.npz" % name))
     if "status" in g.files and g["status"][k] != 0:
         return None                                               # (the oracle itself did not converge there: not a golden point)
@@ -34,9 +36,11 @@ def run(case):
     mass, k1 = (float(g["mass"][k]), float(g["k1"][k])) if per else (float(g["mass"]), float(g["k1"]))
     out = None
     for method in ("trust-constr", "SLSQP"):
-        r = cross_check(N, g["x0"][k], g["com_ref"][k], g["foot_ref"][k], g["gamma"][k], mass, k1, g["X"][k], g["U"][k], method=method,
-                        u0_metric=u0_err)
+        Xs, Us = (g["X"][k], g["U"][k]) if alt is None else (g["X_alt"][k][alt], g["U_alt"][k][alt])
+        r = cross_check(N, g["x0"][k], g["com_ref"][k], g["foot_ref"][k], g["gamma"][k], mass, k1, Xs, Us, method=method, u0_metric=u0_err)
         r.update(golden=name, N=N, tick=int(g["ticks"][k]), index=int(k), mass=mass, k1=k1)
+        if alt is not None:
+            r.update(alt=int(alt))
         ok = r["cost_err"] <= COST_TOL and r["x1_err"] <= X1_TOL and r["u0_err"] <= U0_TOL and r["viol"] <= 1.1e-8
         if out is None or ok:
             out = r
@@ -53,6 +57,7 @@ def main():
         cases += [(name, N, k) for k in range(len(g["ticks"]))]
     g = np.load(os.path.join(HERE, "golden_N60.npz"))
     cases += [("N60", 60, list(g["ticks"]).index(t)) for t in N60_TICKS]
+    cases += [("N60", 60, list(g["ticks"]).index(t), a) for t, a in N60_ALTS]
     with Pool(8) as pool:
         res = [r for r in pool.map(run, cases, chunksize=1) if r is not None]
     with open(os.path.join(HERE, "scipy_pin.json"), "w") as f:
