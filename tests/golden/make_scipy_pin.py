@@ -20,7 +20,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FILES = [("N10", 10), ("N20", 20), ("payload_N10", 10), ("perturbed_N20", 20)]
 N60_TICKS = (805, 1500, 1910)          # push window, mid walk, last valid tick: 1.5 - 2.5 minutes each (ticks 230 / 262 did not finish in 40)
-N60_ALTS = ((150, 2), (230, 2))        # (tick, index into X_alt / U_alt): the lower-cost KKT point scipy moves to from the primary one (6 / 10 minutes)
+# stored ALTERNATIVE KKT points (golden file, horizon, tick, index into X_alt / U_alt).  N = 60: the lower-cost points scipy moves to from the
+# primary ones (6 / 10 minutes).  Not listed: N = 60 tick 1500 alternative 2 -- started next to it scipy goes to the primary point instead
+ALTS = (("N20", 20, 255, 1), ("N20", 20, 759, 1), ("N60", 60, 150, 2), ("N60", 60, 230, 2))
 
 
 def run(case):
@@ -57,7 +59,8 @@ def main():
         cases += [(name, N, k) for k in range(len(g["ticks"]))]
     g = np.load(os.path.join(HERE, "golden_N60.npz"))
     cases += [("N60", 60, list(g["ticks"]).index(t)) for t in N60_TICKS]
-    cases += [("N60", 60, list(g["ticks"]).index(t), a) for t, a in N60_ALTS]
+    for name, N, t, a in ALTS:
+        cases.append((name, N, list(np.load(os.path.join(HERE, "golden_%s.npz" % name))["ticks"]).index(t), a))
     with Pool(8) as pool:
         res = [r for r in pool.map(run, cases, chunksize=1) if r is not None]
     with open(os.path.join(HERE, "scipy_pin.json"), "w") as f:
